@@ -1,0 +1,152 @@
+// Error plumbing, device guard, packed-blob layout, pack entry point and the
+// debug dot-matrix entry point.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+#include "engine_launch.cuh"
+
+namespace amb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return AMB_OK;
+  return set_error(AMB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(cudaGetLastError(), what);
+}
+
+DeviceGuard::DeviceGuard(int dev) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error(AMB_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    ok = false;
+    return;
+  }
+  if (dev < 0 || dev >= n) {
+    set_error(AMB_ERR_ARG, "device index %d out of range [0,%d)", dev, n);
+    ok = false;
+    return;
+  }
+  if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+  if (prev != dev && cudaSetDevice(dev) != cudaSuccess) {
+    set_error(AMB_ERR_CUDA, "cudaSetDevice(%d) failed", dev);
+    ok = false;
+  }
+}
+DeviceGuard::~DeviceGuard() {
+  if (ok && prev >= 0) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+}
+
+int sm_count(int dev) {
+  static std::mutex mu;
+  static int cache[64] = {0};
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  return n;
+}
+
+PackedLayout packed_layout(long long n_rows, int d) {
+  PackedLayout L;
+  L.rows_pad = round_up_ll(n_rows > 0 ? n_rows : 1, kRowPad);
+  L.kpad = static_cast<int>(round_up_ll(d, kBlockK));
+  L.kb_count = L.kpad / kBlockK;
+  L.plane_halfs = L.rows_pad * L.kpad;
+  L.off_lo = static_cast<size_t>(L.plane_halfs) * 2;
+  L.off_inv = L.off_lo * 2;
+  L.off_norm = L.off_inv + static_cast<size_t>(L.rows_pad) * 4;
+  L.bytes = L.off_norm + static_cast<size_t>(L.rows_pad) * 4;
+  L.bytes = static_cast<size_t>(round_up_ll(static_cast<long long>(L.bytes), 256));
+  return L;
+}
+
+PackedPtrs packed_ptrs(void* blob, long long n_rows, int d) {
+  PackedLayout L = packed_layout(n_rows, d);
+  PackedPtrs p;
+  uint8_t* b = static_cast<uint8_t*>(blob);
+  p.planes = reinterpret_cast<__half*>(b);
+  p.plane_halfs = L.plane_halfs;
+  p.inv_scale = reinterpret_cast<float*>(b + L.off_inv);
+  p.norm = reinterpret_cast<float*>(b + L.off_norm);
+  p.rows_pad = L.rows_pad;
+  p.kb_count = L.kb_count;
+  return p;
+}
+
+}  // namespace amb
+
+using namespace amb;
+
+extern "C" {
+
+int amb_version(void) { return 100; }
+const char* amb_last_error(void) { return g_err; }
+long long amb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t amb_packed_bytes(long long n, int d) {
+  if (n < 0 || d <= 0) return 0;
+  return packed_layout(n, d).bytes;
+}
+
+int amb_pack(int dev, amb_stream_t stream, const void* X, int dtype, long long n, int d,
+             long long ld, void* packed) {
+  if (!packed || (n > 0 && !X) || n < 0 || d <= 0 || ld < d)
+    return set_error(AMB_ERR_ARG, "amb_pack: bad argument (n=%lld d=%d ld=%lld)", n, d, ld);
+  DeviceGuard guard(dev);
+  if (!guard.ok) return AMB_ERR_CUDA;
+  PackedPtrs p = packed_ptrs(packed, n, d);
+  return launch_pack(static_cast<cudaStream_t>(stream), X, dtype, ld, d, n, nullptr, n, 0,
+                     p.rows_pad, p.planes, p.plane_halfs, p.kb_count, p.inv_scale, p.norm);
+}
+
+int amb_debug_dot_matrix(int dev, amb_stream_t stream, const void* packed_a, long long na,
+                         const void* packed_b, long long nb, int d, float* C, long long ldc,
+                         unsigned lbo, unsigned sbo) {
+  if (!packed_a || !packed_b || !C || na <= 0 || nb <= 0 || d <= 0 || ldc < 0)
+    return set_error(AMB_ERR_ARG, "amb_debug_dot_matrix: bad argument");
+  DeviceGuard guard(dev);
+  if (!guard.ok) return AMB_ERR_CUDA;
+  PackedPtrs a = packed_ptrs(const_cast<void*>(packed_a), na, d);
+  PackedPtrs b = packed_ptrs(const_cast<void*>(packed_b), nb, d);
+  EngineGeom g{};
+  g.a_planes = a.planes;
+  g.b_planes = b.planes;
+  g.a_plane_halfs = a.plane_halfs;
+  g.b_plane_halfs = b.plane_halfs;
+  g.kb_count = a.kb_count;
+  g.a_rb0 = nullptr;
+  g.b_rb0 = nullptr;
+  g.n_problems = 1;
+  g.n_rt = static_cast<int>(a.rows_pad / kTileM);
+  g.n_ct = static_cast<int>(b.rows_pad / kTileN);
+  g.n_split = 1;
+  g.lbo_bytes = lbo ? lbo : 128;
+  g.sbo_bytes = sbo ? sbo : 512;
+  DumpEpi epi{a.inv_scale, b.inv_scale, C, ldc, na, nb, ldc == 0 ? 1 : 0};
+  return launch_engine(static_cast<cudaStream_t>(stream), dev, g, epi, "pair_engine<dump>");
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+// Epilogue functors for the pair engine (see the concept in pair_engine.cuh).
+// Thread = one row of the 128 x 256 tile; `acc` holds 32 consecutive columns of
+// that row as raw fp32 bits.  acc * inv_scale_a[row] * inv_scale_b[col] is the
+// dot product <x_row, y_col>.
+#pragma once
+#include "internal.cuh"
+#include "pair_engine.cuh"
+
+namespace amb {
+
+__device__ __forceinline__ float f32(uint32_t bits) { return __uint_as_float(bits); }
+constexpr float kInf = __builtin_huge_valf();
+
+// ----------------------------------------------------------------- debug dump
+struct DumpEpi {
+  static constexpr int kColVecs = 1;
+  const float* inv_a;
+  const float* inv_b;
+  float* C;
+  long long ldc;
+  long long na, nb;
+  int checksum_only;       // 1: C[a_row] = sum_j dot (timing runs; no N x M write)
+  struct Row { float isr; long long a_row; float sum; };
+  __device__ const float* colvec_ptr(int) const { return inv_b; }
+  __device__ void row_begin(Row& r, const ItemCoord&, long long a_row) const {
+    r.isr = inv_a[a_row];
+    r.a_row = a_row;
+    r.sum = 0.f;
+  }
+  __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
+                        long long b_row0) const {
+    if (r.a_row >= na) return;
+    if (checksum_only) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r.sum += f32(acc[j]) * cv[0][c0 + j] * r.isr;
+      return;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (b_row0 + j < nb) C[r.a_row * ldc + b_row0 + j] = f32(acc[j]) * cv[0][c0 + j] * r.isr;
+    }
+  }
+  __device__ void row_end(Row& r, const ItemCoord&, int, long long, int, int) const {
+    if (checksum_only && r.a_row < na) C[r.a_row] = r.sum;
+  }
+};
+
+// --------------------------------------------------------- kernel distance sums
+// Problems come in triples per subset: 3s+0 = K(f1,f1), 3s+1 = K(f2,f2),
+// 3s+2 = K(f1,f2)  (kd.py:119-122).  The diagonal of the two symmetric blocks is
+// left out here, which is kd.py:62-63's  K.sum(axis=1) - diag.  Each epilogue
+// warp writes one fp64 partial per work item: partial[item*4 + quarter].
+struct KdEpi {
+  static constexpr int kColVecs = 1;
+  const float* inv_a;
+  const float* inv_b;
+  int kernel_type;
+  double gamma, coef0;
+  int degree;
+  double rbf_scale;          // -1 / (2 sigma^2)
+  const float* norm_a;       // for rbf
+  const float* norm_b;
+  int m_valid;               // rows/cols per problem that are real samples
+  double* partial;
+  struct Row { double sum; double gr; float na; int row_in_problem; bool valid; bool sym; };
+  __device__ const float* colvec_ptr(int) const { return inv_b; }
+  __device__ void row_begin(Row& r, const ItemCoord& c, long long a_row) const {
+    r.row_in_problem = c.rt * kTileM + static_cast<int>(a_row % kTileM);
+    r.valid = r.row_in_problem < m_valid;
+    r.sym = (c.problem % 3) != 2;
+    r.sum = 0.0;
+    const double isr = static_cast<double>(inv_a[a_row]);
+    r.gr = (kernel_type == AMB_KERNEL_POLY ? gamma : 1.0) * isr;
+    r.na = norm_a ? norm_a[a_row] : 0.f;
+  }
+  __device__ __forceinline__ double kval(const Row& r, float acc, float isc, long long b_row) const {
+    const double q = static_cast<double>(acc * isc);   // power-of-two scaling: exact
+    if (kernel_type == AMB_KERNEL_POLY) {
+      const double u = fma(q, r.gr, coef0);
+      double p = u;
+      for (int e = 1; e < degree; ++e) p *= u;
+      return degree == 0 ? 1.0 : p;
+    } else {
+      // rbf_kernel (kd.py:86-109): exp(-|x-y|^2 / (2 sigma^2))
+      double d2 = static_cast<double>(r.na) + static_cast<double>(norm_b[b_row]) - 2.0 * q * r.gr;
+      d2 = d2 < 0 ? 0 : d2;
+      return exp(d2 * rbf_scale);
+    }
+  }
+  __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0,
+                        int col0, long long b_row0) const {
+    if (!r.valid) return;
+    const bool edge = (col0 + 32 > m_valid) || (r.sym && col0 <= r.row_in_problem && r.row_in_problem < col0 + 32);
+    if (!edge && kernel_type == AMB_KERNEL_POLY && degree == 3) {
+      double s0 = 0, s1 = 0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const double u0 = fma(static_cast<double>(f32(acc[j]) * cv[0][c0 + j]), r.gr, coef0);
+        const double u1 = fma(static_cast<double>(f32(acc[j + 1]) * cv[0][c0 + j + 1]), r.gr, coef0);
+        s0 = fma(u0 * u0, u0, s0);
+        s1 = fma(u1 * u1, u1, s1);
+      }
+      r.sum += s0 + s1;
+    } else {
+      double s = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = col0 + j;
+        if (col >= m_valid) continue;
+        if (r.sym && col == r.row_in_problem) continue;
+        s += kval(r, f32(acc[j]), cv[0][c0 + j], b_row0 + j);
+      }
+      r.sum += s;
+    }
+  }
+  __device__ void row_end(Row& r, const ItemCoord&, int item, long long, int quarter, int lane) const {
+    double s = r.valid ? r.sum : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) partial[static_cast<long long>(item) * 4 + quarter] = s;
+  }
+};
+
+// ------------------------------------------------------------ error band
+// The tensor-core dot product q~ differs from the exact <x, y> by at most
+//   kBandDot * |x| |y|
+// (operand split 2^-22 twice, dropped lo*lo 2^-22, and 96 accumulate steps that
+// each truncate to fp32: measured bias -2.7e-6 on all-positive data, bound
+// 96 * 2^-23 = 1.1e-5, doubled for the MMA-internal summation), and the fp32
+// epilogue arithmetic adds at most kBandAbs * (|x|^2 + |y|^2).  Every comparison
+// the tensor-core pass makes is therefore only trusted outside this band;
+// pairs inside it are re-evaluated exactly (fp64) by the refine kernels.
+constexpr float kBandDot = 2.4e-5f;
+constexpr float kBandAbs = 1.0e-6f;
+__host__ __device__ inline float band_key(float nrm_x, float nrm_y_max) {
+  // bound on |t~ - t| for t = |y|^2 - 2<x,y>
+  return 2.0f * kBandDot * sqrtf(nrm_x) * sqrtf(nrm_y_max) + kBandAbs * (nrm_x + nrm_y_max);
+}
+
+// -------------------------------------------------- per-row (k+1)-smallest lists
+// Ranking key for row i over columns j:  t_ij = |y_j|^2 - 2 <x_i, y_j>
+// (d_ij^2 = |x_i|^2 + t_ij).  Each thread keeps its row's K smallest approximate
+// keys, with their column indices, sorted in registers across the whole column
+// sweep; one list per (split, row) leaves the kernel.  K exceeds k+1 by a margin
+// so that the refine kernel can certify that the exact (k+1)-th neighbour is
+// among the kept candidates.
+template <int K>
+struct TopkEpi {
+  static constexpr int kColVecs = 2;   // 0: inv_scale_b, 1: norm_b (+inf on padding)
+  const float* inv_a;
+  const float* inv_b;
+  const float* norm_b;
+  float* keys;             // [n_split][list_rows][K]
+  int* cols;               // [n_split][list_rows][K]   (-1 = empty)
+  long long list_rows;     // rows covered by this launch (multiple of 128)
+  long long a_row_base;    // packed row of list row 0
+  struct Row { float m2isr; float v[K]; int c[K]; };
+  __device__ const float* colvec_ptr(int v) const { return v == 0 ? inv_b : norm_b; }
+  __device__ void row_begin(Row& r, const ItemCoord&, long long a_row) const {
+    r.m2isr = -2.0f * inv_a[a_row];
+#pragma unroll
+    for (int i = 0; i < K; ++i) { r.v[i] = kInf; r.c[i] = -1; }
+  }
+  __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
+                        long long b_row0) const {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float q = f32(acc[j]) * cv[0][c0 + j];
+      const float t = fmaf(q, r.m2isr, cv[1][c0 + j]);
+      if (t < r.v[K - 1]) {
+        r.v[K - 1] = t;
+        r.c[K - 1] = static_cast<int>(b_row0) + j;
+#pragma unroll
+        for (int i = K - 1; i > 0; --i) {
+          const bool sw = r.v[i] < r.v[i - 1];
+          const float va = r.v[i - 1], vb = r.v[i];
+          const int ca = r.c[i - 1], cb = r.c[i];
+          r.v[i - 1] = sw ? vb : va;
+          r.v[i] = sw ? va : vb;
+          r.c[i - 1] = sw ? cb : ca;
+          r.c[i] = sw ? ca : cb;
+        }
+      }
+    }
+  }
+  __device__ void row_end(Row& r, const ItemCoord& c, int, long long a_row, int, int) const {
+    const long long o = (static_cast<long long>(c.split) * list_rows + (a_row - a_row_base)) * K;
+#pragma unroll
+    for (int i = 0; i < K; ++i) { keys[o + i] = r.v[i]; cols[o + i] = r.c[i]; }
+  }
+};
+
+// ------------------------------------------------------- neighbourhood counts
+// Row i = reference sample, column j = candidate (prdc.py:34-48).
+//   in_ref (i,j):  d_ij^2 < r_ref_i^2   <=>  t_ij = |y_j|^2 - 2<x,y>  <  r_ref_i^2 - |x_i|^2  =: A_i
+//   in_cand(i,j):  d_ij^2 < r_cand_j^2  <=>  u_ij = |x_i|^2 - 2<x,y>  <  r_cand_j^2 - |y_j|^2 =: B_j
+// Thresholds come in pairs (lo, hi) = (A - band, A + band): below lo the pair is a
+// certain hit, in [lo, hi) it is appended to the uncertain list and decided later
+// in fp64.  lo = hi = -inf on padding rows / columns, |y_j|^2 = +inf on padding.
+struct PairEntry { uint32_t i; uint32_t j_kind; };   // j_kind: bit 31 = 1 -> in_cand test
+
+struct CountEpi {
+  static constexpr int kColVecs = 3;   // 0: inv_scale_b, 1: norm_b, 2: B_hi
+  const float* inv_a;
+  const float* norm_a;
+  const float* a_lo;       // indexed by packed A row
+  const float* a_hi;
+  const float* inv_b;
+  const float* norm_b;
+  const float* b_lo;       // indexed by packed B row
+  const float* b_hi;
+  int32_t* col_count;      // [m], atomically incremented
+  uint8_t* row_recall;     // [rows of this launch], relative to a_row_base
+  uint8_t* row_cover;
+  long long a_row_base;
+  long long a_row_end;     // packed A rows >= this are padding
+  PairEntry* list;         // uncertain pairs
+  unsigned long long* list_count;
+  unsigned long long list_cap;
+  struct Row { float m2isr, nx, Alo, Ahi; bool rec, cov; uint32_t i; };
+  __device__ const float* colvec_ptr(int v) const { return v == 0 ? inv_b : (v == 1 ? norm_b : b_hi); }
+  __device__ void row_begin(Row& r, const ItemCoord&, long long a_row) const {
+    r.m2isr = -2.0f * inv_a[a_row];
+    r.nx = norm_a[a_row];
+    r.Alo = a_lo[a_row];
+    r.Ahi = a_hi[a_row];
+    r.rec = false;
+    r.cov = false;
+    r.i = static_cast<uint32_t>(a_row);
+  }
+  __device__ __forceinline__ void push(uint32_t i, uint32_t j_kind) const {
+    const unsigned long long pos = atomicAdd(list_count, 1ull);
+    if (pos < list_cap) list[pos] = PairEntry{i, j_kind};
+  }
+  __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
+                        long long b_row0) const {
+    bool any_ref = false, any_cand = false;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float q = f32(acc[j]) * cv[0][c0 + j];
+      const float t = fmaf(q, r.m2isr, cv[1][c0 + j]);
+      const float u = fmaf(q, r.m2isr, r.nx);
+      any_ref |= (t < r.Ahi);
+      any_cand |= (u < cv[2][c0 + j]);
+    }
+    if (__any_sync(0xffffffffu, any_ref)) {
+      // rare: some row of this warp may have a candidate inside its ball in this chunk
+      const int lane = threadIdx.x & 31;
+      int mine = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float q = f32(acc[j]) * cv[0][c0 + j];
+        const float t = fmaf(q, r.m2isr, cv[1][c0 + j]);
+        const bool sure = t < r.Alo;
+        if (!sure && t < r.Ahi) push(r.i, static_cast<uint32_t>(b_row0 + j));
+        r.cov |= sure;
+        const unsigned b = __ballot_sync(0xffffffffu, sure);
+        if (lane == j) mine = __popc(b);
+      }
+      if (mine) atomicAdd(col_count + b_row0 + lane, mine);
+    }
+    if (any_cand) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float q = f32(acc[j]) * cv[0][c0 + j];
+        const float u = fmaf(q, r.m2isr, r.nx);
+        if (u < cv[2][c0 + j]) {
+          if (u < b_lo[b_row0 + j]) r.rec = true;
+          else push(r.i, static_cast<uint32_t>(b_row0 + j) | 0x80000000u);
+        }
+      }
+    }
+  }
+  __device__ void row_end(Row& r, const ItemCoord&, int, long long a_row, int, int) const {
+    if (a_row < a_row_end) {
+      if (r.rec) row_recall[a_row - a_row_base] = 1;
+      if (r.cov) row_cover[a_row - a_row_base] = 1;
+    }
+  }
+};
+
+}  // namespace amb

@@ -1,0 +1,55 @@
+// Library-internal declarations shared by the .cu translation units.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/amb200.h"
+#include "packed.cuh"
+
+namespace amb {
+
+// Thread-local last-error text behind amb_last_error().
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);
+int check_cuda(cudaError_t e, const char* what);
+
+// Sets the calling thread's current device for the duration of a call and
+// restores the previous one, so the library never depends on (or disturbs)
+// the caller's current device.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev);
+  ~DeviceGuard();
+};
+
+int sm_count(int dev);
+
+// Layout of a packed blob (see packed.cuh): [hi plane][lo plane][inv_scale][norm].
+struct PackedLayout {
+  long long rows_pad;
+  int kpad;
+  int kb_count;
+  long long plane_halfs;
+  size_t off_lo, off_inv, off_norm, bytes;
+};
+PackedLayout packed_layout(long long n_rows, int d);
+
+struct PackedPtrs {
+  __half* planes;
+  long long plane_halfs;
+  float* inv_scale;
+  float* norm;
+  long long rows_pad;
+  int kb_count;
+};
+PackedPtrs packed_ptrs(void* blob, long long n_rows, int d);
+
+int launch_pack(cudaStream_t stream, const void* src, int dtype, long long ld, int d,
+                long long n_src_rows, const int* gather, long long n_valid, long long row0,
+                long long n_rows_out, __half* planes, long long plane_halfs, int kb_count,
+                float* inv_scale, float* norm);
+
+}  // namespace amb

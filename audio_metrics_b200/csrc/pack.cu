@@ -1,0 +1,138 @@
+// Pack kernel: fp32/fp64 rows -> scaled fp16 hi/lo planes in the tensor-core
+// shared-memory image (see packed.cuh), plus per-row inverse scale and norm.
+// HBM-bound pre-pass: reads n*d*sizeof(T) once (rows are read twice, the second
+// time from L1/L2), writes 4 bytes per element.
+#include "internal.cuh"
+
+namespace amb {
+
+template <typename T>
+__device__ __forceinline__ float to_scaled_hi_lo(T x, T scale, __half& hi, __half& lo);
+
+template <>
+__device__ __forceinline__ float to_scaled_hi_lo<float>(float x, float scale, __half& hi,
+                                                        __half& lo) {
+  float v = x * scale;  // exact: power-of-two scale
+  hi = __float2half_rn(v);
+  float rem = v - __half2float(hi);  // exact in fp32
+  lo = __float2half_rn(rem);
+  return __half2float(hi) + __half2float(lo);  // may round, only used for the norm via double below
+}
+template <>
+__device__ __forceinline__ float to_scaled_hi_lo<double>(double x, double scale, __half& hi,
+                                                         __half& lo) {
+  double v = x * scale;
+  hi = __double2half(v);
+  double rem = v - static_cast<double>(__half2float(hi));
+  lo = __double2half(rem);
+  return 0.f;
+}
+
+// One warp owns one 8-row group (lane = c*8 + r: row r of the group, k-chunk c
+// of each 32-wide k block), so every store instruction of the warp writes 512
+// contiguous bytes of a plane.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const T* __restrict__ src, long long ld, int d, long long n_src_rows,
+                 const int* __restrict__ gather,  // nullable; <0 => zero row
+                 long long n_valid,               // rows >= n_valid (pre-gather index) are padding
+                 long long row0, long long n_rows_out, __half* __restrict__ planes,
+                 long long plane_halfs, int kb_count, float* __restrict__ inv_scale,
+                 float* __restrict__ norm) {
+  const int lane = threadIdx.x & 31;
+  const int r = lane & 7, c = lane >> 3;
+  const long long group = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (group * 8 >= n_rows_out) return;
+  const long long out_row = row0 + group * 8 + r;   // packed row this lane writes
+  const long long rel_row = group * 8 + r;          // index into gather / source order
+  long long src_row = -1;
+  if (rel_row < n_valid) {
+    src_row = gather ? static_cast<long long>(gather[rel_row]) : rel_row;
+    if (src_row >= n_src_rows) src_row = -1;
+  }
+  const T* rowp = src_row >= 0 ? src + src_row * ld : nullptr;
+
+  // pass 1: row max magnitude
+  T amax = 0;
+  if (rowp) {
+    for (int kb = 0; kb < kb_count; ++kb) {
+      const int k0 = kb * kBlockK + c * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + e;
+        T v = k < d ? rowp[k] : T(0);
+        v = v < 0 ? -v : v;
+        amax = v > amax ? v : amax;
+      }
+    }
+  }
+  {
+    T o = __shfl_xor_sync(0xffffffffu, amax, 8);
+    amax = o > amax ? o : amax;
+    o = __shfl_xor_sync(0xffffffffu, amax, 16);
+    amax = o > amax ? o : amax;
+  }
+  int ex = 0;
+  if (amax > 0 && amax < T(3.0e38)) frexp(static_cast<double>(amax), &ex);  // amax = f*2^ex, f in [.5,1)
+  int sh = 15 - ex;                       // amax * 2^sh in [2^14, 2^15)
+  sh = sh > 120 ? 120 : (sh < -120 ? -120 : sh);
+  const T scale = static_cast<T>(ldexp(1.0, sh));
+  const double inv = ldexp(1.0, -sh);
+
+  // pass 2: split, store, norm
+  double nrm = 0.0;
+  const long long rb = out_row / kBlockRows;
+  const int rin = static_cast<int>(out_row % kBlockRows);
+  const long long chunk_row_off = ((static_cast<long long>(rin >> 3) * 4 + c) * 8 + (rin & 7)) * 8;
+  for (int kb = 0; kb < kb_count; ++kb) {
+    const int k0 = kb * kBlockK + c * 8;
+    alignas(16) __half h[8];
+    alignas(16) __half l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + e;
+      T v = (rowp && k < d) ? rowp[k] : T(0);
+      to_scaled_hi_lo<T>(v, scale, h[e], l[e]);
+      const double xt = static_cast<double>(__half2float(h[e])) + static_cast<double>(__half2float(l[e]));
+      nrm += xt * xt;
+    }
+    const long long off = (rb * kb_count + kb) * kChunkHalfs + chunk_row_off;
+    *reinterpret_cast<uint4*>(planes + off) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(planes + plane_halfs + off) = *reinterpret_cast<const uint4*>(l);
+  }
+  nrm += __shfl_xor_sync(0xffffffffu, nrm, 8);
+  nrm += __shfl_xor_sync(0xffffffffu, nrm, 16);
+  if (c == 0) {
+    if (rowp) {
+      inv_scale[out_row] = static_cast<float>(inv);
+      norm[out_row] = static_cast<float>(nrm * inv * inv);
+    } else {
+      inv_scale[out_row] = 1.0f;
+      norm[out_row] = __int_as_float(0x7f800000);  // +inf: padding row
+    }
+  }
+}
+
+int launch_pack(cudaStream_t stream, const void* src, int dtype, long long ld, int d,
+                long long n_src_rows, const int* gather, long long n_valid, long long row0,
+                long long n_rows_out, __half* planes, long long plane_halfs, int kb_count,
+                float* inv_scale, float* norm) {
+  if (n_rows_out <= 0) return 0;
+  const long long groups = n_rows_out / 8;
+  const int threads = 256;
+  const long long blocks = (groups * 32 + threads - 1) / threads;
+  if (dtype == AMB_F32) {
+    pack_rows_kernel<float><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        static_cast<const float*>(src), ld, d, n_src_rows, gather, n_valid, row0, n_rows_out,
+        planes, plane_halfs, kb_count, inv_scale, norm);
+  } else if (dtype == AMB_F64) {
+    pack_rows_kernel<double><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        static_cast<const double*>(src), ld, d, n_src_rows, gather, n_valid, row0, n_rows_out,
+        planes, plane_halfs, kb_count, inv_scale, norm);
+  } else {
+    return set_error(AMB_ERR_ARG, "pack: dtype must be AMB_F32 or AMB_F64");
+  }
+  return check_launch("pack_rows_kernel");
+}
+
+}  // namespace amb

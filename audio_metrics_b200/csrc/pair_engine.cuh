@@ -1,0 +1,249 @@
+// The all-pairs engine: a persistent, warp-specialised tcgen05 kernel that forms
+// 128 x 256 tiles of  X * Y^T  in tensor memory and hands every finished tile to
+// an epilogue functor while the next tile is being multiplied.  No N x M matrix
+// is ever written: the functors reduce tiles to kernel sums (KD), per-row
+// (k+1)-smallest lists (radii) or neighbourhood counts (PRDC).
+//
+// Precision: each operand is the fp16 pair (hi, lo) of packed.cuh and every
+// k-step issues three MMAs  hi*hi + hi*lo + lo*hi  into one fp32 accumulator,
+// i.e. a dot product of the 22-bit operands (the dropped lo*lo term is 2^-22
+// relative).  This is what makes the tensor-core distances usable for exact
+// neighbourhood counts and for the 1e-4 KD tolerance; a single fp16 pass is not.
+//
+// CTA = 192 threads:  warp 0 bulk-copy producer | warp 1 MMA issuer (+ TMEM
+// owner) | warps 2..5 epilogue (one TMEM lane quarter each; thread = tile row).
+// Pipelines: smem ring full/empty (producer <-> MMA), TMEM double buffer
+// full/empty (MMA <-> epilogue).  Work item = (problem, row tile, column split);
+// a CTA walks items blockIdx.x, +gridDim.x, ... and, inside an item, all column
+// tiles of its split, so per-row state lives in registers across the sweep.
+#pragma once
+#include "packed.cuh"
+#include "tc05.cuh"
+
+namespace amb {
+
+constexpr int kTileM = 128;
+constexpr int kTileN = 256;
+constexpr int kStages = 4;
+constexpr int kStageBytes = 6 * kChunkBytes;          // A hi,lo + B hi(2),lo(2) = 48 KiB
+constexpr int kEngineThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kMaxColVecs = 3;
+constexpr uint32_t kTmemCols = 512;                    // two 256-column accumulators
+
+struct EngineGeom {
+  // operands
+  const __half* a_planes;
+  const __half* b_planes;
+  long long a_plane_halfs;
+  long long b_plane_halfs;
+  int kb_count;              // k blocks of 32
+  // problems: problem p uses A row blocks [a_rb0[p], +n_rt) and B row blocks
+  // [b_rb0[p], +2*n_ct); nullptr tables mean a single problem starting at 0.
+  const int* a_rb0;
+  const int* b_rb0;
+  int a_rb_base;             // added to every A row block index (row shards)
+  int b_rb_base;
+  int n_problems;
+  int n_rt;                  // row tiles (128) per problem
+  int n_ct;                  // column tiles (256) per problem
+  int n_split;               // column splits per (problem, row tile)
+  // debug knobs (descriptor strides), normally 128 / 512
+  uint32_t lbo_bytes;
+  uint32_t sbo_bytes;
+};
+
+struct EngineSmem {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad_;
+  float colvec[2][kMaxColVecs][kTileN];
+};
+
+constexpr size_t kEngineSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + sizeof(EngineSmem);
+
+struct ItemCoord {
+  int problem, rt, split, ct_begin, ct_end;
+};
+
+__device__ __forceinline__ ItemCoord decode_item(const EngineGeom& g, int item) {
+  ItemCoord c;
+  c.split = item % g.n_split;
+  int t = item / g.n_split;
+  c.rt = t % g.n_rt;
+  c.problem = t / g.n_rt;
+  c.ct_begin = static_cast<int>(static_cast<long long>(g.n_ct) * c.split / g.n_split);
+  c.ct_end = static_cast<int>(static_cast<long long>(g.n_ct) * (c.split + 1) / g.n_split);
+  return c;
+}
+
+// Epilogue concept:
+//   struct Epi {
+//     static constexpr int kColVecs;                 // column vectors staged per tile
+//     struct Row;                                    // per-thread (= per tile row) state
+//     const float* colvec_ptr(int v) const;          // global array, indexed by packed B row
+//     void row_begin(Row&, const ItemCoord&, long long a_row /*packed A row*/) const;
+//     void chunk(Row&, const uint32_t (&acc)[32], const float (*cv)[kTileN], int col_in_tile,
+//                int col_in_problem, long long b_row0 /*packed B row of chunk column 0*/) const;
+//     void row_end(Row&, const ItemCoord&, int item, long long a_row, int quarter, int lane) const;
+//   };
+
+template <class Epi>
+__global__ void __launch_bounds__(kEngineThreads, 1)
+pair_engine_kernel(const EngineGeom g, const Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  EngineSmem* sh = reinterpret_cast<EngineSmem*>(smem + size_t(kStages) * kStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_items = g.n_problems * g.n_rt * g.n_split;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sh->full[s], 1);
+      mbar_init(&sh->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&sh->tmem_full[a], 1);
+      mbar_init(&sh->tmem_empty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&sh->tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(g, item);
+        const long long a_rb = (g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + c.rt;
+        const long long b_rb_base = (g.b_rb0 ? g.b_rb0[c.problem] : 0) + g.b_rb_base;
+        const __half* a_src = g.a_planes + a_rb * g.kb_count * kChunkHalfs;
+        for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
+          const __half* b_src = g.b_planes + (b_rb_base + 2ll * ct) * g.kb_count * kChunkHalfs;
+          const long long b_next = static_cast<long long>(g.kb_count) * kChunkHalfs;
+          for (int kb = 0; kb < g.kb_count; ++kb) {
+            mbar_wait(&sh->empty[s], ph ^ 1);
+            uint8_t* st = stage_base + size_t(s) * kStageBytes;
+            mbar_expect_tx(&sh->full[s], kStageBytes);
+            const long long ko = static_cast<long long>(kb) * kChunkHalfs;
+            bulk_g2s(st + 0 * kChunkBytes, a_src + ko, kChunkBytes, &sh->full[s]);
+            bulk_g2s(st + 1 * kChunkBytes, a_src + g.a_plane_halfs + ko, kChunkBytes, &sh->full[s]);
+            bulk_g2s(st + 2 * kChunkBytes, b_src + ko, kChunkBytes, &sh->full[s]);
+            bulk_g2s(st + 3 * kChunkBytes, b_src + b_next + ko, kChunkBytes, &sh->full[s]);
+            bulk_g2s(st + 4 * kChunkBytes, b_src + g.b_plane_halfs + ko, kChunkBytes, &sh->full[s]);
+            bulk_g2s(st + 5 * kChunkBytes, b_src + g.b_plane_halfs + b_next + ko, kChunkBytes,
+                     &sh->full[s]);
+            if (++s == kStages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kTileM, kTileN);
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(g, item);
+        for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
+          mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kTileN;
+          for (int kb = 0; kb < g.kb_count; ++kb) {
+            mbar_wait(&sh->full[s], ph);
+            tc_fence_after();
+            const uint32_t st = smem_u32(stage_base + size_t(s) * kStageBytes);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint32_t koff = ks * 256;   // two 8-wide k chunks of 128 B
+              const uint64_t a_hi = make_kmajor_desc(st + 0 * kChunkBytes + koff, g.lbo_bytes, g.sbo_bytes);
+              const uint64_t a_lo = make_kmajor_desc(st + 1 * kChunkBytes + koff, g.lbo_bytes, g.sbo_bytes);
+              const uint64_t b_hi = make_kmajor_desc(st + 2 * kChunkBytes + koff, g.lbo_bytes, g.sbo_bytes);
+              const uint64_t b_lo = make_kmajor_desc(st + 4 * kChunkBytes + koff, g.lbo_bytes, g.sbo_bytes);
+              mma_f16_ss(d_tmem, a_hi, b_lo, idesc, (kb | ks) != 0 ? 1u : 0u);
+              mma_f16_ss(d_tmem, a_lo, b_hi, idesc, 1u);
+              mma_f16_ss(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
+            tc_commit(&sh->empty[s]);
+            if (++s == kStages) { s = 0; ph ^= 1; }
+          }
+          tc_commit(&sh->tmem_full[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_ph ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
+    const int row_in_tile = quarter * 32 + lane;
+    const int epi_tid = threadIdx.x - 64;         // 0..127
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    int cvbuf = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item(g, item);
+      const long long a_row = ((g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + c.rt) * static_cast<long long>(kTileM) + row_in_tile;
+      const long long b_row_base = static_cast<long long>((g.b_rb0 ? g.b_rb0[c.problem] : 0) + g.b_rb_base) * kBlockRows;
+      typename Epi::Row row;
+      epi.row_begin(row, c, a_row);
+      for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
+        const long long b_row0 = b_row_base + static_cast<long long>(ct) * kTileN;
+        // stage this tile's column vectors (2 columns per thread per vector)
+#pragma unroll
+        for (int v = 0; v < Epi::kColVecs; ++v) {
+          const float* src = epi.colvec_ptr(v) + b_row0;
+          sh->colvec[cvbuf][v][epi_tid] = __ldg(src + epi_tid);
+          sh->colvec[cvbuf][v][epi_tid + 128] = __ldg(src + epi_tid + 128);
+        }
+        named_bar_sync(1, kEpiThreads);
+        mbar_wait(&sh->tmem_full[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc) * kTileN +
+                                (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTileN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_addr + c0, r);
+          tmem_wait_ld();
+          epi.chunk(row, r, sh->colvec[cvbuf], c0, ct * kTileN + c0, b_row0 + c0);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
+        cvbuf ^= 1;
+      }
+      epi.row_end(row, c, item, a_row, quarter, lane);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace amb

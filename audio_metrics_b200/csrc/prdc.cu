@@ -1,0 +1,515 @@
+// PRDC on the pair engine: k-NN radii (prdc.py:4-14) and neighbourhood counts
+// (prdc.py:18-50).  The tensor-core sweep is a filter with a proven error band
+// (epilogues.cuh); every decision that falls inside the band is re-made from the
+// original rows in fp64 by the refine kernels below, so radii are the correctly
+// rounded exact distances and counts are the exact-arithmetic counts.
+#include <vector>
+
+#include "engine_launch.cuh"
+
+namespace amb {
+
+// ------------------------------------------------------------------ helpers
+__global__ void max_norm_kernel(const float* __restrict__ norm, long long n, float* out_max) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = norm[i];
+    if (v < kInf) m = fmaxf(m, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out_max), __float_as_int(m));  // m >= 0
+}
+
+template <typename T>
+__device__ __forceinline__ double exact_sqdist_warp(const T* __restrict__ x, const T* __restrict__ y, int d,
+                                                    int lane) {
+  double s = 0.0;
+  for (int k = lane; k < d; k += 32) {
+    const double df = static_cast<double>(x[k]) - static_cast<double>(y[k]);
+    s = fma(df, df, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+// Distance exactly as a correctly rounded fp32 evaluation would give it; ties in
+// exact arithmetic stay ties, which keeps the strict '<' of prdc.py:37-48.
+__device__ __forceinline__ float dist_f32(double d2) { return static_cast<float>(sqrt(d2)); }
+
+// ------------------------------------------------------------- radii: refine
+// One warp per row: merge the per-split candidate lists, keep the Kt best
+// approximate candidates, evaluate their exact squared distances, take the
+// (k+1)-th smallest, and certify it against the band.  Uncertified rows go to
+// the brute-force list.
+template <typename T>
+__global__ void __launch_bounds__(256)
+knn_refine_kernel(const T* __restrict__ X, long long ld, int d, long long n, long long row0,
+                  long long nrows, int k, int Kt, int n_split, long long list_rows,
+                  const float* __restrict__ keys, const int* __restrict__ cols,
+                  const float* __restrict__ norm, const float* __restrict__ max_norm,
+                  float* __restrict__ radii, int* __restrict__ unresolved, int* __restrict__ n_unresolved) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  if (row >= nrows) return;
+  const long long i = row0 + row;
+  const T* xi = X + i * ld;
+  // --- select the Kt smallest approximate candidates over all splits (lane c keeps the c-th)
+  const int n_cand = n_split * Kt;
+  float sel_key = kInf;
+  int sel_col = -1;
+  float last_key = -kInf;
+  int last_col = -1;
+  for (int r = 0; r < Kt; ++r) {
+    float best = kInf;
+    int best_col = 0x7fffffff;
+    for (int c = lane; c < n_cand; c += 32) {
+      const int sp = c / Kt, e = c - sp * Kt;
+      const long long o = (static_cast<long long>(sp) * list_rows + row) * Kt + e;
+      const float kv = keys[o];
+      const int cc = cols[o];
+      if (cc < 0) continue;
+      const bool after = (kv > last_key) || (kv == last_key && cc > last_col);
+      if (after && (kv < best || (kv == best && cc < best_col))) { best = kv; best_col = cc; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, best_col, o);
+      if (ob < best || (ob == best && oc < best_col)) { best = ob; best_col = oc; }
+    }
+    if (best_col == 0x7fffffff) break;   // fewer than Kt candidates exist
+    last_key = best;
+    last_col = best_col;
+    if (lane == r) { sel_key = best; sel_col = best_col; }
+  }
+  // --- exact squared distances of the selected candidates (lane c <- candidate c)
+  double my_d2 = __longlong_as_double(0x7ff0000000000000ll);
+  int n_sel = 0;
+  for (int c = 0; c < Kt; ++c) {
+    const int col = __shfl_sync(0xffffffffu, sel_col, c);
+    if (col < 0) break;
+    const double d2 = exact_sqdist_warp(xi, X + static_cast<long long>(col) * ld, d, lane);
+    if (lane == c) my_d2 = d2;
+    n_sel = c + 1;
+  }
+  // --- (k+1)-th smallest exact value among them: rank by (value, lane)
+  int rank = 0;
+  for (int c = 0; c < n_sel; ++c) {
+    const double o = __shfl_sync(0xffffffffu, my_d2, c);
+    rank += (o < my_d2 || (o == my_d2 && c < lane)) ? 1 : 0;
+  }
+  const unsigned who = __ballot_sync(0xffffffffu, lane < n_sel && rank == k);
+  double r2 = 0.0;
+  bool ok = who != 0;
+  if (ok) r2 = __shfl_sync(0xffffffffu, my_d2, __ffs(who) - 1);
+  // --- certificate: every column that was not kept has approximate key >= t_last (the
+  // largest kept key), hence exact d^2 >= |x_i|^2 + t_last - band.  Complete lists
+  // (fewer than Kt candidates overall) are trivially certified.
+  const float t_last = __shfl_sync(0xffffffffu, sel_key, Kt - 1);
+  const int last_sel = __shfl_sync(0xffffffffu, sel_col, Kt - 1);
+  if (ok && last_sel >= 0) {
+    const float nx = norm[i];
+    const float band = band_key(nx, *max_norm);
+    const double bound = static_cast<double>(nx) + static_cast<double>(t_last) - static_cast<double>(band);
+    if (!(r2 < bound)) ok = false;
+  }
+  if (lane == 0) {
+    radii[row] = who != 0 ? dist_f32(r2) : kInf;
+    if (!ok) {
+      const int p = atomicAdd(n_unresolved, 1);
+      unresolved[p] = static_cast<int>(row);   // capacity = nrows
+    }
+  }
+}
+
+// Brute force for rows the certificate rejected (near-ties beyond the kept
+// margin, heavy duplication): exact distances to all n rows, (k+1)-th smallest.
+// One CTA per unresolved row, persistent over the list; the work is capped by
+// max_rows so that pathological inputs (everything tied) stay bounded — rows
+// beyond the cap keep the refine kernel's value, whose error is below the band.
+template <typename T>
+__global__ void __launch_bounds__(256)
+knn_bruteforce_kernel(const T* __restrict__ X, long long ld, int d, long long n, long long row0, int k,
+                      const int* __restrict__ unresolved, const int* __restrict__ n_unresolved,
+                      int max_rows, float* __restrict__ radii) {
+  __shared__ double s_best[8][32];   // per warp: k+1 smallest (k+1 <= 32)
+  __shared__ double s_merge[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double INF = __longlong_as_double(0x7ff0000000000000ll);
+  int count = *n_unresolved;
+  if (count > max_rows) count = max_rows;
+  for (int u = blockIdx.x; u < count; u += gridDim.x) {
+    const long long row = unresolved[u];
+    const T* xi = X + (row0 + row) * ld;
+    // each warp scans columns warp, warp+8, ...; lane l of the warp holds the l-th smallest so far
+    double mine = INF;
+    for (long long j = warp; j < n; j += 8) {
+      const double d2 = exact_sqdist_warp(xi, X + j * ld, d, lane);
+      // insert d2 into the sorted-by-lane list (ascending with lane), keep k+1 entries
+      const double kth = __shfl_sync(0xffffffffu, mine, k);
+      if (d2 < kth) {
+        const unsigned below = __ballot_sync(0xffffffffu, mine <= d2);   // lanes whose value stays
+        const int pos = __popc(below);                                   // insertion lane
+        const double up = __shfl_up_sync(0xffffffffu, mine, 1);
+        if (lane == pos) mine = d2;
+        else if (lane > pos) mine = up;
+      }
+    }
+    s_best[warp][lane] = lane <= k ? mine : INF;
+    __syncthreads();
+    if (warp == 0) {
+      // merge 8 sorted lists: lane l picks the overall rank-l element by counting
+      double v[8];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v[w] = s_best[w][lane];
+      // rank of each of my 8 values among all 256 values
+      for (int w = 0; w < 8; ++w) {
+        int rank = 0;
+        for (int w2 = 0; w2 < 8; ++w2)
+          for (int l2 = 0; l2 < 32; ++l2) {
+            const double o = s_best[w2][l2];
+            rank += (o < v[w] || (o == v[w] && (w2 * 32 + l2) < (w * 32 + lane))) ? 1 : 0;
+          }
+        if (rank == k && v[w] < INF) s_merge[0] = v[w];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) radii[row] = dist_f32(s_merge[0]);
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------- counts: thresholds
+__global__ void prdc_thresholds_kernel(const float* __restrict__ norm, const float* __restrict__ radii,
+                                       long long n_valid, long long rows_pad,
+                                       const float* __restrict__ other_max_norm, float* __restrict__ lo,
+                                       float* __restrict__ hi) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= rows_pad) return;
+  if (i >= n_valid) { lo[i] = -kInf; hi[i] = -kInf; return; }
+  const float nx = norm[i];
+  const float r = radii[i];
+  const float r2 = r * r;
+  // band on the key plus slack for the fp32 rounding of r^2, |x|^2 and of the
+  // final fp32 distance the refine kernel compares (3e-7 ~ 2.5 ulp)
+  const float band = band_key(nx, *other_max_norm) + 3e-7f * (r2 + nx);
+  const float a = r2 - nx;
+  lo[i] = a - band;
+  hi[i] = a + band;
+}
+
+// -------------------------------------------------------------- counts: refine
+template <typename T>
+__global__ void __launch_bounds__(256)
+prdc_exact_pairs_kernel(const T* __restrict__ R, long long ldr, const T* __restrict__ C, long long ldc, int d,
+                        const float* __restrict__ r_ref, const float* __restrict__ r_cand,
+                        const PairEntry* __restrict__ list, const unsigned long long* __restrict__ list_count,
+                        unsigned long long list_cap, long long row0, int32_t* __restrict__ col_count,
+                        uint8_t* __restrict__ row_recall, uint8_t* __restrict__ row_cover) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long count = *list_count;
+  if (count > list_cap) count = list_cap;
+  const unsigned long long warps = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 5;
+  for (unsigned long long e = (blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x) >> 5;
+       e < count; e += warps) {
+    const PairEntry p = list[e];
+    const long long i = p.i;
+    const long long j = p.j_kind & 0x7fffffffu;
+    const bool cand_test = (p.j_kind >> 31) != 0;
+    const double d2 = exact_sqdist_warp(R + i * ldr, C + j * ldc, d, lane);
+    if (lane == 0) {
+      const float D = dist_f32(d2);
+      if (cand_test) {
+        if (D < r_cand[j]) row_recall[i - row0] = 1;
+      } else if (D < r_ref[i]) {
+        atomicAdd(col_count + j, 1);
+        row_cover[i - row0] = 1;
+      }
+    }
+  }
+}
+
+__global__ void prdc_reduce_kernel(const int32_t* __restrict__ col_count, long long m,
+                                   const uint8_t* __restrict__ row_recall, const uint8_t* __restrict__ row_cover,
+                                   long long nrows, unsigned long long* __restrict__ totals) {
+  unsigned long long hit = 0, sum = 0, rec = 0, cov = 0;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long t0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (col_count)
+    for (long long j = t0; j < m; j += stride) {
+      const int c = col_count[j];
+      hit += c > 0;
+      sum += static_cast<unsigned long long>(c);
+    }
+  for (long long i = t0; i < nrows; i += stride) {
+    if (row_recall) rec += row_recall[i] != 0;
+    if (row_cover) cov += row_cover[i] != 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    hit += __shfl_xor_sync(0xffffffffu, hit, o);
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    rec += __shfl_xor_sync(0xffffffffu, rec, o);
+    cov += __shfl_xor_sync(0xffffffffu, cov, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (hit) atomicAdd(totals + 0, hit);
+    if (sum) atomicAdd(totals + 1, sum);
+    if (rec) atomicAdd(totals + 2, rec);
+    if (cov) atomicAdd(totals + 3, cov);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int pick_kt(int k) {
+  const int need = k + 1 + 2;
+  if (need <= 8) return 8;
+  if (need <= 16) return 16;
+  if (need <= 32) return 32;
+  return 0;
+}
+
+// Column splits per row tile: items are dealt round-robin to the persistent CTAs
+// (item -> CTA item % grid), so simulate that deal for every candidate split
+// count and keep the one with the smallest makespan in column tiles.
+static int pick_split(int dev, long long n_rt, long long n_ct) {
+  const int sms = sm_count(dev);
+  const int s_max = static_cast<int>(n_ct < 32 ? n_ct : 32);
+  if (n_rt >= 64ll * sms) return 1;   // many waves: tail is negligible
+  int best_s = 1;
+  long long best_span = -1;
+  std::vector<long long> load;
+  for (int s = 1; s <= s_max; ++s) {
+    const long long items = n_rt * s;
+    const int grid = static_cast<int>(items < sms ? items : sms);
+    load.assign(grid, 0);
+    for (long long it = 0; it < items; ++it) {
+      const long long sp = it % s;
+      const long long tiles = n_ct * (sp + 1) / s - n_ct * sp / s;
+      load[it % grid] += tiles + 1;   // +1: per-item fixed cost (row state, list write)
+    }
+    long long span = 0;
+    for (long long v : load) span = v > span ? v : span;
+    if (best_span < 0 || span < best_span) { best_span = span; best_s = s; }
+  }
+  return best_s;
+}
+
+struct KnnWs {
+  float* keys;
+  int* cols;
+  int* unresolved;
+  int* n_unresolved;
+  float* max_norm;
+  size_t bytes;
+};
+static KnnWs knn_ws(void* ws, long long nrows, int Kt, int n_split) {
+  const long long list_rows = round_up_ll(nrows, kTileM);
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  size_t off = 0;
+  KnnWs w;
+  auto take = [&](size_t bytes) { uint8_t* p = b ? b + off : nullptr; off += static_cast<size_t>(round_up_ll(bytes, 256)); return p; };
+  w.keys = reinterpret_cast<float*>(take(static_cast<size_t>(n_split) * list_rows * Kt * 4));
+  w.cols = reinterpret_cast<int*>(take(static_cast<size_t>(n_split) * list_rows * Kt * 4));
+  w.unresolved = reinterpret_cast<int*>(take(static_cast<size_t>(nrows > 0 ? nrows : 1) * 4));
+  w.n_unresolved = reinterpret_cast<int*>(take(256));
+  w.max_norm = reinterpret_cast<float*>(take(256));
+  w.bytes = off;
+  return w;
+}
+
+template <int K>
+static int run_topk(cudaStream_t st, int dev, EngineGeom& g, const PackedPtrs& p, const KnnWs& w,
+                    long long list_rows, long long a_row_base) {
+  TopkEpi<K> epi{p.inv_scale, p.inv_scale, p.norm, w.keys, w.cols, list_rows, a_row_base};
+  return launch_engine(st, dev, g, epi, "pair_engine<topk>");
+}
+
+}  // namespace amb
+
+using namespace amb;
+
+extern "C" {
+
+size_t amb_knn_ws_bytes(long long nrows, long long n, int k) {
+  const int Kt = pick_kt(k);
+  if (!Kt || nrows < 0 || n <= 0) return 0;
+  // worst-case split count is 32 (pick_split), independent of the device
+  return knn_ws(nullptr, nrows, Kt, 32).bytes;
+}
+
+int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long long ld, const void* packed,
+                  long long n, int d, long long row0, long long nrows, int k, float* radii, void* ws,
+                  size_t ws_bytes) {
+  if (!X || !packed || !radii || n <= 0 || d <= 0 || nrows < 0 || row0 < 0 || row0 + nrows > n || ld < d)
+    return set_error(AMB_ERR_ARG, "amb_knn_radii: bad argument");
+  if (k < 1 || k + 1 > n)
+    return set_error(AMB_ERR_ARG, "amb_knn_radii: k=%d needs at least k+1 rows (n=%lld); the reference's "
+                                  "kthvalue raises here too", k, n);
+  if (row0 % kTileM != 0) return set_error(AMB_ERR_ARG, "amb_knn_radii: row0 must be a multiple of 128");
+  if (n >= (1ll << 31)) return set_error(AMB_ERR_ARG, "amb_knn_radii: n must be < 2^31");
+  const int Kt = pick_kt(k);
+  if (!Kt) return set_error(AMB_ERR_ARG, "amb_knn_radii: k=%d not supported (k <= 29)", k);
+  if (dtype != AMB_F32 && dtype != AMB_F64) return set_error(AMB_ERR_ARG, "amb_knn_radii: bad dtype");
+  if (nrows == 0) return AMB_OK;
+  DeviceGuard guard(dev);
+  if (!guard.ok) return AMB_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PackedPtrs p = packed_ptrs(const_cast<void*>(packed), n, d);
+  const long long n_rt = (nrows + kTileM - 1) / kTileM;
+  const long long n_ct = p.rows_pad / kTileN;
+  const int n_split = pick_split(dev, n_rt, n_ct);
+  KnnWs w = knn_ws(ws, nrows, Kt, n_split);
+  if (!ws || ws_bytes < w.bytes) return set_error(AMB_ERR_WS, "amb_knn_radii: workspace %zu < %zu", ws_bytes, w.bytes);
+  const long long list_rows = round_up_ll(nrows, kTileM);
+  int rc = check_cuda(cudaMemsetAsync(w.n_unresolved, 0, 512, st), "memset");   // n_unresolved + max_norm
+  if (rc) return rc;
+  max_norm_kernel<<<64, 256, 0, st>>>(p.norm, p.rows_pad, w.max_norm);
+  if ((rc = check_launch("max_norm_kernel"))) return rc;
+
+  EngineGeom g{};
+  g.a_planes = p.planes;
+  g.b_planes = p.planes;
+  g.a_plane_halfs = p.plane_halfs;
+  g.b_plane_halfs = p.plane_halfs;
+  g.kb_count = p.kb_count;
+  g.a_rb_base = static_cast<int>(row0 / kTileM);
+  g.n_problems = 1;
+  g.n_rt = static_cast<int>(n_rt);
+  g.n_ct = static_cast<int>(n_ct);
+  g.n_split = n_split;
+  g.lbo_bytes = 128;
+  g.sbo_bytes = 512;
+  if (Kt == 8) rc = run_topk<8>(st, dev, g, p, w, list_rows, row0);
+  else if (Kt == 16) rc = run_topk<16>(st, dev, g, p, w, list_rows, row0);
+  else rc = run_topk<32>(st, dev, g, p, w, list_rows, row0);
+  if (rc) return rc;
+
+  const unsigned blocks = static_cast<unsigned>((nrows * 32 + 255) / 256);
+  const int bf_blocks = 4 * sm_count(dev);
+  // brute-force budget: ~2e11 fp64 multiply-adds
+  long long max_rows = static_cast<long long>(2e11 / (static_cast<double>(n) * d));
+  if (max_rows > nrows) max_rows = nrows;
+  if (dtype == AMB_F32) {
+    const float* Xf = static_cast<const float*>(X);
+    knn_refine_kernel<float><<<blocks, 256, 0, st>>>(Xf, ld, d, n, row0, nrows, k, Kt, n_split, list_rows, w.keys,
+                                                     w.cols, p.norm, w.max_norm, radii, w.unresolved, w.n_unresolved);
+    if ((rc = check_launch("knn_refine_kernel"))) return rc;
+    knn_bruteforce_kernel<float><<<bf_blocks, 256, 0, st>>>(Xf, ld, d, n, row0, k, w.unresolved, w.n_unresolved,
+                                                            static_cast<int>(max_rows), radii);
+  } else {
+    const double* Xd = static_cast<const double*>(X);
+    knn_refine_kernel<double><<<blocks, 256, 0, st>>>(Xd, ld, d, n, row0, nrows, k, Kt, n_split, list_rows, w.keys,
+                                                      w.cols, p.norm, w.max_norm, radii, w.unresolved, w.n_unresolved);
+    if ((rc = check_launch("knn_refine_kernel"))) return rc;
+    knn_bruteforce_kernel<double><<<bf_blocks, 256, 0, st>>>(Xd, ld, d, n, row0, k, w.unresolved, w.n_unresolved,
+                                                             static_cast<int>(max_rows), radii);
+  }
+  return check_launch("knn_bruteforce_kernel");
+}
+
+long long amb_prdc_list_cap(long long n_ref, long long m) {
+  long long cap = 16 * (n_ref + m);
+  return cap < (1ll << 20) ? (1ll << 20) : cap;
+}
+
+size_t amb_prdc_ws_bytes(long long n_ref, long long m) {
+  if (n_ref <= 0 || m <= 0) return 0;
+  const long long rp = round_up_ll(n_ref, kRowPad), cp = round_up_ll(m, kRowPad);
+  return static_cast<size_t>(round_up_ll((2 * rp + 2 * cp) * 4, 256) + 512 + amb_prdc_list_cap(n_ref, m) * 8);
+}
+
+int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, const void* packed_ref,
+                    long long n_ref, const float* r_ref, const void* C, long long ldc,
+                    const void* packed_cand, long long m, const float* r_cand, int d, int dtype,
+                    long long row0, long long nrows, int32_t* col_count, uint8_t* row_recall,
+                    uint8_t* row_cover, long long* n_uncertain, void* ws, size_t ws_bytes) {
+  if (!R || !C || !packed_ref || !packed_cand || !r_ref || !r_cand || !col_count || !row_recall || !row_cover ||
+      n_ref <= 0 || m <= 0 || d <= 0 || row0 < 0 || nrows < 0 || row0 + nrows > n_ref || ldr < d || ldc < d)
+    return set_error(AMB_ERR_ARG, "amb_prdc_counts: bad argument");
+  if (row0 % kTileM != 0) return set_error(AMB_ERR_ARG, "amb_prdc_counts: row0 must be a multiple of 128");
+  if (n_ref >= (1ll << 31) || m >= (1ll << 31)) return set_error(AMB_ERR_ARG, "amb_prdc_counts: sizes must be < 2^31");
+  if (dtype != AMB_F32 && dtype != AMB_F64) return set_error(AMB_ERR_ARG, "amb_prdc_counts: bad dtype");
+  const size_t need = amb_prdc_ws_bytes(n_ref, m);
+  if (!ws || ws_bytes < need) return set_error(AMB_ERR_WS, "amb_prdc_counts: workspace %zu < %zu", ws_bytes, need);
+  if (nrows == 0) return AMB_OK;
+  DeviceGuard guard(dev);
+  if (!guard.ok) return AMB_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PackedPtrs pr = packed_ptrs(const_cast<void*>(packed_ref), n_ref, d);
+  PackedPtrs pc = packed_ptrs(const_cast<void*>(packed_cand), m, d);
+  // workspace carve-up
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  float* a_lo = reinterpret_cast<float*>(b);
+  float* a_hi = a_lo + pr.rows_pad;
+  float* b_lo = a_hi + pr.rows_pad;
+  float* b_hi = b_lo + pc.rows_pad;
+  uint8_t* q = b + round_up_ll((2 * pr.rows_pad + 2 * pc.rows_pad) * 4, 256);
+  unsigned long long* list_count = reinterpret_cast<unsigned long long*>(q);
+  float* max_ref = reinterpret_cast<float*>(q + 64);
+  float* max_cand = reinterpret_cast<float*>(q + 128);
+  PairEntry* list = reinterpret_cast<PairEntry*>(q + 512);
+  const long long cap = amb_prdc_list_cap(n_ref, m);
+
+  int rc;
+  if ((rc = check_cuda(cudaMemsetAsync(q, 0, 512, st), "memset"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(row_recall, 0, nrows, st), "memset"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(row_cover, 0, nrows, st), "memset"))) return rc;
+  max_norm_kernel<<<64, 256, 0, st>>>(pr.norm, pr.rows_pad, max_ref);
+  if ((rc = check_launch("max_norm_kernel"))) return rc;
+  max_norm_kernel<<<64, 256, 0, st>>>(pc.norm, pc.rows_pad, max_cand);
+  if ((rc = check_launch("max_norm_kernel"))) return rc;
+  prdc_thresholds_kernel<<<static_cast<unsigned>((pr.rows_pad + 255) / 256), 256, 0, st>>>(
+      pr.norm, r_ref, n_ref, pr.rows_pad, max_cand, a_lo, a_hi);
+  if ((rc = check_launch("prdc_thresholds_kernel"))) return rc;
+  prdc_thresholds_kernel<<<static_cast<unsigned>((pc.rows_pad + 255) / 256), 256, 0, st>>>(
+      pc.norm, r_cand, m, pc.rows_pad, max_ref, b_lo, b_hi);
+  if ((rc = check_launch("prdc_thresholds_kernel"))) return rc;
+
+  EngineGeom g{};
+  g.a_planes = pr.planes;
+  g.b_planes = pc.planes;
+  g.a_plane_halfs = pr.plane_halfs;
+  g.b_plane_halfs = pc.plane_halfs;
+  g.kb_count = pr.kb_count;
+  g.a_rb_base = static_cast<int>(row0 / kTileM);
+  g.n_problems = 1;
+  g.n_rt = static_cast<int>((nrows + kTileM - 1) / kTileM);
+  g.n_ct = static_cast<int>(pc.rows_pad / kTileN);
+  g.n_split = pick_split(dev, g.n_rt, g.n_ct);
+  g.lbo_bytes = 128;
+  g.sbo_bytes = 512;
+  CountEpi epi{pr.inv_scale, pr.norm, a_lo, a_hi, pc.inv_scale, pc.norm, b_lo, b_hi, col_count, row_recall,
+               row_cover, row0, row0 + nrows, list, list_count, static_cast<unsigned long long>(cap)};
+  if ((rc = launch_engine(st, dev, g, epi, "pair_engine<count>"))) return rc;
+
+  const int blocks = 8 * sm_count(dev);
+  if (dtype == AMB_F32)
+    prdc_exact_pairs_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(R), ldr,
+                                                           static_cast<const float*>(C), ldc, d, r_ref, r_cand, list,
+                                                           list_count, cap, row0, col_count, row_recall, row_cover);
+  else
+    prdc_exact_pairs_kernel<double><<<blocks, 256, 0, st>>>(static_cast<const double*>(R), ldr,
+                                                            static_cast<const double*>(C), ldc, d, r_ref, r_cand, list,
+                                                            list_count, cap, row0, col_count, row_recall, row_cover);
+  if ((rc = check_launch("prdc_exact_pairs_kernel"))) return rc;
+  if (n_uncertain)
+    rc = check_cuda(cudaMemcpyAsync(n_uncertain, list_count, 8, cudaMemcpyDeviceToDevice, st), "memcpy");
+  return rc;
+}
+
+int amb_prdc_reduce(int dev, amb_stream_t stream, const int32_t* col_count, long long m,
+                    const uint8_t* row_recall, const uint8_t* row_cover, long long nrows,
+                    long long* totals) {
+  if (!totals || m < 0 || nrows < 0) return set_error(AMB_ERR_ARG, "amb_prdc_reduce: bad argument");
+  DeviceGuard guard(dev);
+  if (!guard.ok) return AMB_ERR_CUDA;
+  prdc_reduce_kernel<<<2 * sm_count(dev), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      col_count, m, row_recall, row_cover, nrows, reinterpret_cast<unsigned long long*>(totals));
+  return check_launch("prdc_reduce_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+/* amb200 — C ABI of the B200-native embedding-set distance path.
+ *
+ * The reference (SonyCSLParis/audio-metrics, pure Python) has no FFI layer: its
+ * boundary for this path is the Python call surface of data.py / metrics/*.py.
+ * Each entry point below is what a binding for one of those functions calls; the
+ * reference interface it replaces is cited as  file:line  (relative to the
+ * reference's src/audio_metrics/).
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, scalars; no torch / C++ types.
+ *  - every call names its CUDA device and stream explicitly; the library never
+ *    relies on the caller's current device and never syncs the default stream.
+ *  - "device-pointer" functions (amb_*): all array arguments are device memory
+ *    on `dev`; work is enqueued on `stream` and the call returns without
+ *    synchronising unless stated.  Scratch memory is caller-provided (`ws`,
+ *    size from the matching *_ws_bytes query); the library allocates nothing.
+ *  - "host-buffer" functions (amb_host_*): array arguments are host memory;
+ *    the call stages them through device memory it allocates and frees itself,
+ *    runs the same kernels, synchronises and returns results in host memory.
+ *    These are what a numpy/ctypes binding of the reference calls directly.
+ *  - return 0 on success, a negative AMB_ERR_* otherwise; amb_last_error() gives
+ *    the calling thread's last message.  There is no CPU fallback: without a
+ *    usable CUDA device every compute call fails with AMB_ERR_CUDA.
+ */
+#ifndef AMB200_H_
+#define AMB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* amb_stream_t; /* a cudaStream_t (0 = legacy default stream) */
+
+enum { AMB_F32 = 0, AMB_F64 = 1 };
+enum {
+  AMB_OK = 0,
+  AMB_ERR_ARG = -1,     /* invalid argument (shape, dtype, k, null pointer) */
+  AMB_ERR_CUDA = -2,    /* CUDA runtime / launch failure, or no device */
+  AMB_ERR_WS = -3,      /* workspace too small */
+  AMB_ERR_NUMERIC = -4  /* iteration failed to converge */
+};
+enum { AMB_KERNEL_POLY = 0, AMB_KERNEL_RBF = 1 };
+
+int amb_version(void);
+const char* amb_last_error(void);
+/* Number of kernels this library has launched in the calling process (for
+ * bench.py's gpu_launches claim). */
+long long amb_launch_count(void);
+
+/* ------------------------------------------------------------------ statistics
+ * AudioMetricsData.add / recompute_stats (data.py:37-58): batch mean and unbiased
+ * covariance, kept here as fp64 raw moments so that batches, GPUs and calls add. */
+
+/* sum[d] += column sums of X, gram[d*d] += X^T X (full symmetric matrix), fp64.
+ * X is [n, d] row-major with leading dimension ld (elements), dtype f32/f64. */
+size_t amb_cov_ws_bytes(long long n, int d);
+int amb_cov_accumulate(int dev, amb_stream_t stream, const void* X, int dtype, long long n, int d,
+                       long long ld, double* sum, double* gram, void* ws, size_t ws_bytes);
+/* mean = sum/n;  cov = (gram - n mean mean^T)/(n-1), zeros when n == 1
+ * (data.py:39-44: torch.mean, torch.cov(correction=1), zeros for n == 1). */
+int amb_cov_finalize(int dev, amb_stream_t stream, long long n, int d, const double* sum,
+                     const double* gram, double* mean, double* cov);
+/* Chan pairwise merge of (n1, mean1, cov1) += (n2, mean2, cov2), in place in the
+ * first operand (data.py:77-94 _update_stats).  scratch_mean: [d] fp64 scratch. */
+int amb_stats_merge(int dev, amb_stream_t stream, int d, long long n1, double* mean1, double* cov1,
+                    long long n2, const double* mean2, const double* cov2, double* scratch_mean);
+
+/* --------------------------------------------------------------- Frechet distance
+ * frechet_distance / _frechet_distance (metrics/fad.py:8-31):
+ *   |mu_x - mu_y|^2 + tr S_x + tr S_y - 2 sum_i sqrt(lambda_i(S_x S_y)),
+ * for `batch` independent pairs.  mu_*: [batch, d], cov_*: [batch, d, d], fp64,
+ * out: [batch] fp64.  The eigenvalue sum is evaluated as the nuclear norm of
+ * F_y^T F_x with S = F F^T (one-sided Jacobi, fp64). */
+size_t amb_frechet_ws_bytes(int batch, int d);
+int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu_x,
+                const double* cov_x, const double* mu_y, const double* cov_y, double* out, void* ws,
+                size_t ws_bytes);
+
+/* --------------------------------------------------------------- packed operands
+ * Embeddings are rewritten once per set into the tensor-core operand format
+ * (two fp16 planes + per-row scale and squared norm); KD and PRDC consume that. */
+size_t amb_packed_bytes(long long n, int d);
+int amb_pack(int dev, amb_stream_t stream, const void* X, int dtype, long long n, int d,
+             long long ld, void* packed);
+
+/* ----------------------------------------------------------------- kernel distance
+ * kernel_distance -> kid_features_to_metric (metrics/kd.py:29-35,127-194) with
+ * polynomial_kernel (kd.py:112-116), kernel_mmd2 (kd.py:119-124) and the unbiased
+ * mmd2 (kd.py:38-83).  F1 [n1,d], F2 [n2,d]; idx [S,2,m] int32 holds, per subset,
+ * the m row indices drawn from F1 then the m drawn from F2 (the host draws them
+ * with numpy's default_rng exactly as kd.py:176,185-186 does).
+ * mmd2_out [S] fp64; stats_out[2] = {mean, population std} (kd.py:189-192). */
+size_t amb_kd_ws_bytes(int S, int m, int d);
+int amb_kd_subsets(int dev, amb_stream_t stream, const void* F1, long long n1, long long ld1,
+                   const void* F2, long long n2, long long ld2, int d, int dtype, const int32_t* idx,
+                   int S, int m, int kernel_type, double gamma, double coef0, int degree,
+                   double sigma, double* mmd2_out, double* stats_out, void* ws, size_t ws_bytes);
+
+/* --------------------------------------------------------------------------- PRDC
+ * Both PRDC entry points use the tensor-core sweep as a filter with a proven
+ * error band and re-decide everything inside the band from the original rows in
+ * fp64, so they also take the unpacked matrix (X / R / C, dtype, leading dim).
+ *
+ * nearest_neighbour_distances (metrics/prdc.py:4-14): radius_i = (k+1)-th
+ * smallest Euclidean distance from row i to all rows of the set (self
+ * included), returned as the correctly rounded fp32 value of the exact distance.
+ * Computes radii for rows [row0, row0+nrows) of the set (row0 % 128 == 0)
+ * against all n rows.  radii: [nrows] fp32.  1 <= k <= 29 and k+1 <= n (the
+ * reference's kthvalue raises for k+1 > n). */
+size_t amb_knn_ws_bytes(long long nrows, long long n, int k);
+int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long long ld,
+                  const void* packed, long long n, int d, long long row0, long long nrows, int k,
+                  float* radii, void* ws, size_t ws_bytes);
+
+/* prdc (metrics/prdc.py:18-50) neighbourhood counts for reference rows
+ * [row0, row0+nrows) (row0 % 128 == 0) against all m candidates, strict '<' on
+ * fp32 distances as in prdc.py:37-48:
+ *   col_count[j]  += #{i in shard : D_ij < r_ref[i]}          (density; >0 => precision)
+ *   row_recall[i]  = any_j  D_ij < r_cand[j]                  (i relative to row0)
+ *   row_cover[i]   = any_j  D_ij < r_ref[i]   (== min_j D_ij < r_ref[i], prdc.py:48)
+ * r_ref: [n_ref] fp32 (indexed by absolute row), r_cand: [m] fp32.
+ * col_count [m] int32 is accumulated and must be zeroed by the caller before the
+ * first shard; row_recall / row_cover [nrows] are overwritten.  n_uncertain
+ * (device int64, nullable) receives the number of pairs that fell inside the
+ * band; if it exceeds amb_prdc_list_cap(n_ref, m) the excess pairs were NOT
+ * re-decided and the caller must treat the result as invalid. */
+size_t amb_prdc_ws_bytes(long long n_ref, long long m);
+long long amb_prdc_list_cap(long long n_ref, long long m);
+int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr,
+                    const void* packed_ref, long long n_ref, const float* r_ref, const void* C,
+                    long long ldc, const void* packed_cand, long long m, const float* r_cand, int d,
+                    int dtype, long long row0, long long nrows, int32_t* col_count,
+                    uint8_t* row_recall, uint8_t* row_cover, long long* n_uncertain, void* ws,
+                    size_t ws_bytes);
+/* totals[4] (int64) += { #cols with count>0, sum of col_count, #rows recalled,
+ * #rows covered } — the numerators of precision, density*k, recall, coverage.
+ * Null array arguments are skipped. */
+int amb_prdc_reduce(int dev, amb_stream_t stream, const int32_t* col_count, long long m,
+                    const uint8_t* row_recall, const uint8_t* row_cover, long long nrows,
+                    long long* totals);
+
+/* -------------------------------------------------------------- host-buffer calls
+ * Same computations with host arrays in and host scalars out (H2D, kernels, D2H
+ * and a stream synchronise inside the call). */
+int amb_host_stats(int dev, const void* X, int dtype, long long n, int d, double* mean,
+                   double* cov);
+int amb_host_frechet(int dev, int d, const double* mu_x, const double* cov_x, const double* mu_y,
+                     const double* cov_y, double* out);
+int amb_host_kd(int dev, const void* F1, long long n1, const void* F2, long long n2, int d,
+                int dtype, const int32_t* idx, int S, int m, double gamma, double coef0, int degree,
+                double* mmd2_out, double* stats_out);
+int amb_host_knn_radii(int dev, const void* X, int dtype, long long n, int d, int k, float* radii);
+/* out[4] = precision, recall, density, coverage (prdc.py:50). */
+int amb_host_prdc(int dev, const void* ref, long long n, const void* cand, long long m, int d,
+                  int dtype, int k, double* out);
+
+/* ------------------------------------------------------------- debug / validation
+ * Full dot-product matrix through the tensor-core engine (small sizes only):
+ * C[i*ldc + j] = <A_i, B_j> from packed operands; with ldc == 0 only the row
+ * sums C[i] = sum_j <A_i, B_j> are written (timing runs).  lbo/sbo override the
+ * shared-memory descriptor strides (0 = library default). */
+int amb_debug_dot_matrix(int dev, amb_stream_t stream, const void* packed_a, long long na,
+                         const void* packed_b, long long nb, int d, float* C, long long ldc,
+                         unsigned lbo, unsigned sbo);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMB200_H_ */
