@@ -24,6 +24,8 @@ SIGNATURES = {
     "amb_version": (_i, []),
     "amb_last_error": (C.c_char_p, []),
     "amb_launch_count": (_ll, []),
+    "amb_profile_enable": (_i, [_i]),
+    "amb_profile_read": (_i, [_vp]),
     "amb_cov_ws_bytes": (_sz, [_ll, _i]),
     "amb_cov_accumulate": (_i, [_i, _vp, _vp, _i, _ll, _i, _ll, _vp, _vp, _vp, _sz]),
     "amb_cov_finalize": (_i, [_i, _vp, _ll, _i, _vp, _vp, _vp, _vp]),

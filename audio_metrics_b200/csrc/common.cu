@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "engine_launch.cuh"
 
@@ -69,6 +70,29 @@ int sm_count(int dev) {
   return n;
 }
 
+struct ProfRec { cudaEvent_t e0, e1; double pairs, flops; };
+static std::mutex g_prof_mu;
+static std::atomic<int> g_prof_on{0};
+static std::vector<ProfRec> g_prof;
+
+void* profile_begin(cudaStream_t stream) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return nullptr;
+  ProfRec* r = new ProfRec{};
+  if (cudaEventCreate(&r->e0) != cudaSuccess || cudaEventCreate(&r->e1) != cudaSuccess) { delete r; return nullptr; }
+  cudaEventRecord(r->e0, stream);
+  return r;
+}
+void profile_end(void* token, cudaStream_t stream, double alg_pairs, double exec_flops) {
+  if (!token) return;
+  ProfRec* r = static_cast<ProfRec*>(token);
+  cudaEventRecord(r->e1, stream);
+  r->pairs = alg_pairs;
+  r->flops = exec_flops;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(*r);
+  delete r;
+}
+
 PackedLayout packed_layout(long long n_rows, int d) {
   PackedLayout L;
   L.rows_pad = round_up_ll(n_rows > 0 ? n_rows : 1, kRowPad);
@@ -105,6 +129,35 @@ extern "C" {
 int amb_version(void) { return 100; }
 const char* amb_last_error(void) { return g_err; }
 long long amb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int amb_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return AMB_OK;
+}
+
+// out[0] = engine launches, out[1] = total device ms, out[2] = algorithmic pairs,
+// out[3] = executed MMA flops.  Waits for the recorded events; clears the log.
+int amb_profile_read(double* out) {
+  if (!out) return set_error(AMB_ERR_ARG, "amb_profile_read: null");
+  std::vector<ProfRec> recs;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    recs.swap(g_prof);
+  }
+  out[0] = out[1] = out[2] = out[3] = 0.0;
+  for (ProfRec& r : recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      out[0] += 1.0;
+      out[1] += ms;
+      out[2] += r.pairs;
+      out[3] += r.flops;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  return AMB_OK;
+}
 
 size_t amb_packed_bytes(long long n, int d) {
   if (n < 0 || d <= 0) return 0;

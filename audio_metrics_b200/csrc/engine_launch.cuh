@@ -9,7 +9,8 @@
 namespace amb {
 
 template <class Epi>
-int launch_engine(cudaStream_t stream, int dev, const EngineGeom& g, const Epi& epi, const char* what) {
+int launch_engine(cudaStream_t stream, int dev, const EngineGeom& g, const Epi& epi, const char* what,
+                  double alg_pairs = 0.0) {
   static std::once_flag once;  // per Epi instantiation
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -25,7 +26,12 @@ int launch_engine(cudaStream_t stream, int dev, const EngineGeom& g, const Epi& 
   if (items <= 0) return AMB_OK;
   const int sms = sm_count(dev);
   const unsigned grid = static_cast<unsigned>(items < sms ? items : sms);
+  // executed MMA work: full tiles, three fp16 MMAs per k step
+  const double exec_flops = static_cast<double>(g.n_problems) * g.n_rt * g.n_ct * (2.0 * kTileM * kTileN) *
+                            (g.kb_count * static_cast<double>(kBlockK)) * 3.0;
+  void* tok = profile_begin(stream);
   pair_engine_kernel<Epi><<<grid, kEngineThreads, kEngineSmemBytes, stream>>>(g, epi);
+  profile_end(tok, stream, alg_pairs, exec_flops);
   return check_launch(what);
 }
 

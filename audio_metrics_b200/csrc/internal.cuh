@@ -27,6 +27,11 @@ struct DeviceGuard {
 
 int sm_count(int dev);
 
+// Optional per-launch timing of the pair engine (amb_profile_*): CUDA events on the
+// launching stream around the kernel.  No-ops unless enabled.
+void* profile_begin(cudaStream_t stream);
+void profile_end(void* token, cudaStream_t stream, double alg_pairs, double exec_flops);
+
 // Layout of a packed blob (see packed.cuh): [hi plane][lo plane][inv_scale][norm].
 struct PackedLayout {
   long long rows_pad;

@@ -144,7 +144,7 @@ int amb_kd_subsets(int dev, amb_stream_t stream, const void* F1, long long n1, l
   epi.norm_b = p.norm;
   epi.m_valid = m;
   epi.partial = w.partial;
-  if ((rc = launch_engine(st, dev, g, epi, "pair_engine<kd>"))) return rc;
+  if ((rc = launch_engine(st, dev, g, epi, "pair_engine<kd>", 3.0 * S * static_cast<double>(m) * m))) return rc;
   kd_finalize_kernel<<<1, 256, static_cast<size_t>(S) * 8, st>>>(w.partial, S, g.n_rt * 4, m, mmd2_out, stats_out);
   return check_launch("kd_finalize_kernel");
 }

@@ -323,9 +323,9 @@ static KnnWs knn_ws(void* ws, long long nrows, int Kt, int n_split) {
 
 template <int K>
 static int run_topk(cudaStream_t st, int dev, EngineGeom& g, const PackedPtrs& p, const KnnWs& w,
-                    long long list_rows, long long a_row_base) {
+                    long long list_rows, long long a_row_base, double alg_pairs) {
   TopkEpi<K> epi{p.inv_scale, p.inv_scale, p.norm, w.keys, w.cols, list_rows, a_row_base};
-  return launch_engine(st, dev, g, epi, "pair_engine<topk>");
+  return launch_engine(st, dev, g, epi, "pair_engine<topk>", alg_pairs);
 }
 
 }  // namespace amb
@@ -383,9 +383,9 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
   g.n_split = n_split;
   g.lbo_bytes = 128;
   g.sbo_bytes = 512;
-  if (Kt == 8) rc = run_topk<8>(st, dev, g, p, w, list_rows, row0);
-  else if (Kt == 16) rc = run_topk<16>(st, dev, g, p, w, list_rows, row0);
-  else rc = run_topk<32>(st, dev, g, p, w, list_rows, row0);
+  if (Kt == 8) rc = run_topk<8>(st, dev, g, p, w, list_rows, row0, static_cast<double>(nrows) * n);
+  else if (Kt == 16) rc = run_topk<16>(st, dev, g, p, w, list_rows, row0, static_cast<double>(nrows) * n);
+  else rc = run_topk<32>(st, dev, g, p, w, list_rows, row0, static_cast<double>(nrows) * n);
   if (rc) return rc;
 
   const unsigned blocks = static_cast<unsigned>((nrows * 32 + 255) / 256);
@@ -484,7 +484,7 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   g.sbo_bytes = 512;
   CountEpi epi{pr.inv_scale, pr.norm, a_lo, a_hi, pc.inv_scale, pc.norm, b_lo, b_hi, col_count, row_recall,
                row_cover, row0, row0 + nrows, list, list_count, static_cast<unsigned long long>(cap)};
-  if ((rc = launch_engine(st, dev, g, epi, "pair_engine<count>"))) return rc;
+  if ((rc = launch_engine(st, dev, g, epi, "pair_engine<count>", static_cast<double>(nrows) * m))) return rc;
 
   const int blocks = 8 * sm_count(dev);
   if (dtype == AMB_F32)

@@ -50,6 +50,12 @@ const char* amb_last_error(void);
  * bench.py's gpu_launches claim). */
 long long amb_launch_count(void);
 
+/* Per-launch device timing of the all-pairs tensor-core kernel (CUDA events on the
+ * launching stream).  amb_profile_read waits for the recorded launches, clears the
+ * log and fills out[4] = { launches, total ms, algorithmic pairs, executed MMA flops }. */
+int amb_profile_enable(int on);
+int amb_profile_read(double* out);
+
 /* ------------------------------------------------------------------ statistics
  * AudioMetricsData.add / recompute_stats (data.py:37-58): batch mean and unbiased
  * covariance, kept here as fp64 raw moments so that batches, GPUs and calls add. */

@@ -1,0 +1,76 @@
+"""world_size-2 gloo test of the row-sharding / reduction logic in
+audio_metrics_b200.dist, with oracle stand-in kernels (no GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from oracle.prdc import cdist_exact
+from audio_metrics_b200.dist import evaluate_sharded, shard_rows
+from audio_metrics_b200.synth import make_sets_numpy
+
+
+def test_shard_rows_cover_and_align():
+    for n in (1, 100, 128, 129, 1000, 200000, 12345):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_rows(n, world, r) for r in range(world)]
+            assert sum(s[1] for s in spans) == n
+            pos = 0
+            for row0, nrows, chunk in spans:
+                assert row0 % 128 == 0 or nrows == 0
+                assert row0 == min(pos, n) or nrows == 0
+                pos += chunk
+            # only the last non-empty shard may be partial -> gathered[:n] is the global array
+            nonempty = [s for s in spans if s[1]]
+            assert all(s[1] == s[2] for s in nonempty[:-1])
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_ref, n_cand, d, k, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle_ops import OracleOps
+        ref, cand = make_sets_numpy(n_ref, n_cand, d, seed=77)
+        r0, rn, _ = shard_rows(n_ref, world, rank)
+        c0, cn, _ = shard_rows(n_cand, world, rank)
+        res = evaluate_sharded(torch.from_numpy(ref[r0:r0 + rn]), torch.from_numpy(cand[c0:c0 + cn]), n_ref, n_cand,
+                               nearest_k=k, ops=OracleOps(), kd_subsets=7, kd_subset_size=60)
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_ref,n_cand", [(300, 200), (130, 257)])
+def test_sharded_equals_single_process(n_ref, n_cand):
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    d, k, world = 32, 4, 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_ref, n_cand, d, k, out), nprocs=world, join=True)
+    ref, cand = make_sets_numpy(n_ref, n_cand, d, seed=77)
+    assert out[0] == out[1]
+    res = out[0]
+    mr, cr, _ = oracle.batch_stats(ref, compute_dtype=np.dtype(np.float64))
+    mc, cc, _ = oracle.batch_stats(cand, compute_dtype=np.dtype(np.float64))
+    assert res["fad"] == pytest.approx(oracle.frechet_from_stats(mc, cc, mr, cr), rel=1e-9)
+    kd = oracle.kernel_distance(cand, ref, subsets=7, subset_size=60, compute_dtype=np.float64)
+    assert res["kernel_distance_mean"] == pytest.approx(kd["kernel_distance_mean"], rel=1e-9)
+    assert res["kernel_distance_std"] == pytest.approx(kd["kernel_distance_std"], rel=1e-9)
+    f32 = lambda a, b: cdist_exact(a, b).astype(np.float32)
+    want = oracle.prdc(ref, cand, k, dist=f32)
+    for key in ("precision", "recall", "density", "coverage"):
+        assert res[key] == pytest.approx(want[key], abs=1e-12)
