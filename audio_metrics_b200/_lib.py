@@ -37,7 +37,7 @@ SIGNATURES = {
     "amb_kd_ws_bytes": (_sz, [_i, _i, _i]),
     "amb_kd_subsets": (_i, [_i, _vp, _vp, _ll, _ll, _vp, _ll, _ll, _i, _i, _vp, _i, _i, _i, _dbl, _dbl, _i,
                             _dbl, _vp, _vp, _vp, _sz]),
-    "amb_knn_ws_bytes": (_sz, [_ll, _ll, _i]),
+    "amb_knn_ws_bytes": (_sz, [_ll, _ll, _i, _i]),
     "amb_knn_radii": (_i, [_i, _vp, _vp, _i, _ll, _vp, _ll, _i, _ll, _ll, _i, _vp, _vp, _sz]),
     "amb_prdc_ws_bytes": (_sz, [_ll, _ll]),
     "amb_prdc_list_cap": (_ll, [_ll, _ll]),

@@ -28,7 +28,7 @@ struct DumpEpi {
     r.sum = 0.f;
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
-                        long long b_row0) const {
+                        long long b_row0, float*) const {
     if (r.a_row >= na) return;
     if (checksum_only) {
 #pragma unroll
@@ -88,7 +88,7 @@ struct KdEpi {
     }
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0,
-                        int col0, long long b_row0) const {
+                        int col0, long long b_row0, float*) const {
     if (!r.valid) return;
     const bool edge = (col0 + 32 > m_valid) || (r.sym && col0 <= r.row_in_problem && r.row_in_problem < col0 + 32);
     if (!edge && kernel_type == AMB_KERNEL_POLY && degree == 3) {
@@ -162,14 +162,48 @@ struct TopkEpi {
     for (int i = 0; i < K; ++i) { r.v[i] = kInf; r.c[i] = -1; }
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
-                        long long b_row0) const {
+                        long long b_row0, float* scratch) const {
+    // branch-free scan first: most chunks hold nothing below the row's current
+    // K-th smallest key
+    float t[32];
+    float m0 = kInf, m1 = kInf, m2 = kInf, m3 = kInf;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float q = f32(acc[j]) * cv[0][c0 + j];
-      const float t = fmaf(q, r.m2isr, cv[1][c0 + j]);
-      if (t < r.v[K - 1]) {
-        r.v[K - 1] = t;
-        r.c[K - 1] = static_cast<int>(b_row0) + j;
+    for (int j = 0; j < 32; j += 4) {
+      t[j + 0] = fmaf(f32(acc[j + 0]) * cv[0][c0 + j + 0], r.m2isr, cv[1][c0 + j + 0]);
+      t[j + 1] = fmaf(f32(acc[j + 1]) * cv[0][c0 + j + 1], r.m2isr, cv[1][c0 + j + 1]);
+      t[j + 2] = fmaf(f32(acc[j + 2]) * cv[0][c0 + j + 2], r.m2isr, cv[1][c0 + j + 2]);
+      t[j + 3] = fmaf(f32(acc[j + 3]) * cv[0][c0 + j + 3], r.m2isr, cv[1][c0 + j + 3]);
+      m0 = fminf(m0, t[j + 0]);
+      m1 = fminf(m1, t[j + 1]);
+      m2 = fminf(m2, t[j + 2]);
+      m3 = fminf(m3, t[j + 3]);
+    }
+    const float tmin = fminf(fminf(m0, m1), fminf(m2, m3));
+    if (__any_sync(0xffffffffu, tmin < r.v[K - 1])) {
+      // some row of the warp takes new candidates.  Each thread builds the bit mask
+      // of its qualifying columns, parks its 32 keys in its private shared-memory
+      // row, and the warp loops while any lane still has a bit to consume (usually
+      // one trip): a lane picks its lowest set column, reloads that key by dynamic
+      // index and inserts it; the threshold tightens as it goes.
+      unsigned mask = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        scratch[j] = t[j];
+        mask |= (t[j] < r.v[K - 1]) ? (1u << j) : 0u;
+      }
+      while (__any_sync(0xffffffffu, mask != 0)) {
+        float key = kInf;
+        int col = -1;
+        if (mask) {
+          const int j = __ffs(mask) - 1;
+          mask &= mask - 1;
+          key = scratch[j];
+          col = static_cast<int>(b_row0) + j;
+        }
+        if (key < r.v[K - 1]) {
+          r.v[K - 1] = key;
+          r.c[K - 1] = col;
+        }
 #pragma unroll
         for (int i = K - 1; i > 0; --i) {
           const bool sw = r.v[i] < r.v[i - 1];
@@ -233,7 +267,7 @@ struct CountEpi {
     if (pos < list_cap) list[pos] = PairEntry{i, j_kind};
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
-                        long long b_row0) const {
+                        long long b_row0, float*) const {
     bool any_ref = false, any_cand = false;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {

@@ -134,7 +134,7 @@ int amb_host_knn_radii(int dev, const void* X, int dtype, long long n, int d, in
   void* dX = h.upload_raw(X, static_cast<size_t>(n) * d * esize(dtype));
   void* packed = h.alloc<uint8_t>(amb_packed_bytes(n, d));
   float* r = h.alloc<float>(n);
-  const size_t wsb = amb_knn_ws_bytes(n, n, k);
+  const size_t wsb = amb_knn_ws_bytes(n, n, d, k);
   void* ws = h.alloc<uint8_t>(wsb);
   if (h.rc) return h.rc;
   h.run(amb_pack(dev, h.st, dX, dtype, n, d, d, packed));
@@ -158,8 +158,8 @@ int amb_host_prdc(int dev, const void* ref, long long n, const void* cand, long 
   uint8_t* rec = h.alloc<uint8_t>(n);
   uint8_t* cov = h.alloc<uint8_t>(n);
   long long* totals = h.alloc<long long>(8);
-  size_t wsb = amb_knn_ws_bytes(n, n, k);
-  const size_t w2 = amb_knn_ws_bytes(m, m, k), w3 = amb_prdc_ws_bytes(n, m);
+  size_t wsb = amb_knn_ws_bytes(n, n, d, k);
+  const size_t w2 = amb_knn_ws_bytes(m, m, d, k), w3 = amb_prdc_ws_bytes(n, m);
   wsb = wsb > w2 ? wsb : w2;
   wsb = wsb > w3 ? wsb : w3;
   void* ws = h.alloc<uint8_t>(wsb);

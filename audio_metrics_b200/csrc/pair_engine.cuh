@@ -54,25 +54,33 @@ struct EngineGeom {
 };
 
 struct EngineSmem {
+  alignas(128) float colvec[2][kMaxColVecs][kTileN];   // bulk-copy destinations: keep 16 B aligned
   uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t cv_full[2];
   uint32_t tmem_base;
   uint32_t pad_;
-  float colvec[2][kMaxColVecs][kTileN];
+  float scratch[kEpiThreads][33];   // per-row spill area for epilogues (stride 33: conflict-free)
 };
 
-constexpr size_t kEngineSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + sizeof(EngineSmem);
+constexpr size_t kEngineSmemBytes = size_t(kStages) * kStageBytes + sizeof(EngineSmem);
 
 struct ItemCoord {
   int problem, rt, split, ct_begin, ct_end;
 };
 
+// Items are numbered split-major: all (problem, row tile) pairs of column split 0
+// first, then split 1, ...  The persistent CTAs deal items round-robin, so at any
+// moment the whole grid sweeps the SAME column split: that split's B operand
+// (sized by the host to fit L2 next to the in-flight A panels) is fetched from
+// HBM once instead of once per row tile.
 __device__ __forceinline__ ItemCoord decode_item(const EngineGeom& g, int item) {
   ItemCoord c;
-  c.split = item % g.n_split;
-  int t = item / g.n_split;
+  const int per_split = g.n_problems * g.n_rt;
+  c.split = item / per_split;
+  const int t = item - c.split * per_split;
   c.rt = t % g.n_rt;
   c.problem = t / g.n_rt;
   c.ct_begin = static_cast<int>(static_cast<long long>(g.n_ct) * c.split / g.n_split);
@@ -87,17 +95,19 @@ __device__ __forceinline__ ItemCoord decode_item(const EngineGeom& g, int item) 
 //     const float* colvec_ptr(int v) const;          // global array, indexed by packed B row
 //     void row_begin(Row&, const ItemCoord&, long long a_row /*packed A row*/) const;
 //     void chunk(Row&, const uint32_t (&acc)[32], const float (*cv)[kTileN], int col_in_tile,
-//                int col_in_problem, long long b_row0 /*packed B row of chunk column 0*/) const;
+//                int col_in_problem, long long b_row0 /*packed B row of chunk column 0*/,
+//                float* scratch /*33 floats of shared memory private to this row*/) const;
 //     void row_end(Row&, const ItemCoord&, int item, long long a_row, int quarter, int lane) const;
 //   };
 
 template <class Epi>
 __global__ void __launch_bounds__(kEngineThreads, 1)
 pair_engine_kernel(const EngineGeom g, const Epi epi) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_base = smem;
-  EngineSmem* sh = reinterpret_cast<EngineSmem*>(smem + size_t(kStages) * kStageBytes);
+  // no pointer laundering here: everything derived from smem_buf stays in the
+  // shared address space for the compiler (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem_buf[];
+  uint8_t* stage_base = smem_buf;
+  EngineSmem* sh = reinterpret_cast<EngineSmem*>(smem_buf + size_t(kStages) * kStageBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,6 +121,7 @@ pair_engine_kernel(const EngineGeom g, const Epi epi) {
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sh->tmem_full[a], 1);
       mbar_init(&sh->tmem_empty[a], 4);
+      mbar_init(&sh->cv_full[a], 1);
     }
     fence_mbar_init();
   }
@@ -126,8 +137,12 @@ pair_engine_kernel(const EngineGeom g, const Epi epi) {
   if (warp == 0) {
     // ------------------------------------------------------------ producer
     if (lane == 0) {
+      // the A row panel is re-read for every column tile of the item: ask L2 to keep it
+      const uint64_t keep = l2_policy_evict_last();
       int s = 0;
       uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const ItemCoord c = decode_item(g, item);
         const long long a_rb = (g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + c.rt;
@@ -136,13 +151,23 @@ pair_engine_kernel(const EngineGeom g, const Epi epi) {
         for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
           const __half* b_src = g.b_planes + (b_rb_base + 2ll * ct) * g.kb_count * kChunkHalfs;
           const long long b_next = static_cast<long long>(g.kb_count) * kChunkHalfs;
+          // this tile's column vectors ride the same engine: 1 KiB bulk copies into
+          // the buffer the epilogue released two tiles ago
+          mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+          mbar_expect_tx(&sh->cv_full[acc], Epi::kColVecs * kTileN * 4);
+#pragma unroll
+          for (int v = 0; v < Epi::kColVecs; ++v)
+            bulk_g2s(sh->colvec[acc][v], epi.colvec_ptr(v) + (b_rb_base + 2ll * ct) * kBlockRows, kTileN * 4,
+                     &sh->cv_full[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_ph ^= 1;
           for (int kb = 0; kb < g.kb_count; ++kb) {
             mbar_wait(&sh->empty[s], ph ^ 1);
             uint8_t* st = stage_base + size_t(s) * kStageBytes;
             mbar_expect_tx(&sh->full[s], kStageBytes);
             const long long ko = static_cast<long long>(kb) * kChunkHalfs;
-            bulk_g2s(st + 0 * kChunkBytes, a_src + ko, kChunkBytes, &sh->full[s]);
-            bulk_g2s(st + 1 * kChunkBytes, a_src + g.a_plane_halfs + ko, kChunkBytes, &sh->full[s]);
+            bulk_g2s_hint(st + 0 * kChunkBytes, a_src + ko, kChunkBytes, &sh->full[s], keep);
+            bulk_g2s_hint(st + 1 * kChunkBytes, a_src + g.a_plane_halfs + ko, kChunkBytes, &sh->full[s], keep);
             bulk_g2s(st + 2 * kChunkBytes, b_src + ko, kChunkBytes, &sh->full[s]);
             bulk_g2s(st + 3 * kChunkBytes, b_src + b_next + ko, kChunkBytes, &sh->full[s]);
             bulk_g2s(st + 4 * kChunkBytes, b_src + g.b_plane_halfs + ko, kChunkBytes, &sh->full[s]);
@@ -198,7 +223,6 @@ pair_engine_kernel(const EngineGeom g, const Epi epi) {
     const int epi_tid = threadIdx.x - 64;         // 0..127
     int acc = 0;
     uint32_t acc_ph = 0;
-    int cvbuf = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const ItemCoord c = decode_item(g, item);
       const long long a_row = ((g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + c.rt) * static_cast<long long>(kTileM) + row_in_tile;
@@ -207,14 +231,7 @@ pair_engine_kernel(const EngineGeom g, const Epi epi) {
       epi.row_begin(row, c, a_row);
       for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
         const long long b_row0 = b_row_base + static_cast<long long>(ct) * kTileN;
-        // stage this tile's column vectors (2 columns per thread per vector)
-#pragma unroll
-        for (int v = 0; v < Epi::kColVecs; ++v) {
-          const float* src = epi.colvec_ptr(v) + b_row0;
-          sh->colvec[cvbuf][v][epi_tid] = __ldg(src + epi_tid);
-          sh->colvec[cvbuf][v][epi_tid + 128] = __ldg(src + epi_tid + 128);
-        }
-        named_bar_sync(1, kEpiThreads);
+        mbar_wait(&sh->cv_full[acc], acc_ph);     // column vectors landed (producer bulk copy)
         mbar_wait(&sh->tmem_full[acc], acc_ph);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc) * kTileN +
@@ -224,14 +241,13 @@ pair_engine_kernel(const EngineGeom g, const Epi epi) {
           uint32_t r[32];
           tmem_ld32(t_addr + c0, r);
           tmem_wait_ld();
-          epi.chunk(row, r, sh->colvec[cvbuf], c0, ct * kTileN + c0, b_row0 + c0);
+          epi.chunk(row, r, sh->colvec[acc], c0, ct * kTileN + c0, b_row0 + c0, sh->scratch[epi_tid]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
         acc ^= 1;
         if (acc == 0) acc_ph ^= 1;
-        cvbuf ^= 1;
       }
       epi.row_end(row, c, item, a_row, quarter, lane);
     }

@@ -3,6 +3,7 @@
 // (epilogues.cuh); every decision that falls inside the band is re-made from the
 // original rows in fp64 by the refine kernels below, so radii are the correctly
 // rounded exact distances and counts are the exact-arithmetic counts.
+#include <cstdlib>
 #include <vector>
 
 #include "engine_launch.cuh"
@@ -264,30 +265,50 @@ __global__ void prdc_reduce_kernel(const int32_t* __restrict__ col_count, long l
 }
 
 // ------------------------------------------------------------------ host side
+// Candidates kept per row.  The margin beyond k+1 is what lets the refine kernel
+// certify its answer: the (k+1)-th exact distance must sit below the Kt-th
+// approximate key by more than the error band.
 static int pick_kt(int k) {
-  const int need = k + 1 + 2;
+  if (k + 1 > 30) return 0;
+  const int need = 2 * (k + 1) + 4;
   if (need <= 8) return 8;
   if (need <= 16) return 16;
-  if (need <= 32) return 32;
-  return 0;
+  return 32;
 }
 
-// Column splits per row tile: items are dealt round-robin to the persistent CTAs
-// (item -> CTA item % grid), so simulate that deal for every candidate split
-// count and keep the one with the smallest makespan in column tiles.
-static int pick_split(int dev, long long n_rt, long long n_ct) {
+// Column splits per row tile.  Items are numbered split-major and dealt round-robin
+// to the persistent CTAs (pair_engine.cuh), so the whole grid sweeps one split
+// at a time.
+//   * Many row tiles (>= 2 per SM): one split.  Every CTA then walks all column
+//     tiles at the MMA-bound pace, the grid stays in lockstep and each B tile is
+//     fetched from HBM about once per wave (measured at 200k x 200k x 512:
+//     5-8 GB of DRAM reads per launch, 98-99 % L2 hit rate, tensor pipe 91 %).
+//     `l2_bytes` > 0 instead sizes splits so the B operand of a split is about
+//     that many bytes (used by the count pass, which measures best that way).
+//   * Few row tiles: split columns so every SM has work, choosing the split
+//     count with the smallest round-robin makespan in column tiles.
+constexpr long long kCountSplitBytes = 16ll << 20;
+static int pick_split(int dev, long long n_rt, long long n_ct, int kb_count, long long l2_bytes) {
   const int sms = sm_count(dev);
-  const int s_max = static_cast<int>(n_ct < 32 ? n_ct : 32);
-  if (n_rt >= 64ll * sms) return 1;   // many waves: tail is negligible
-  int best_s = 1;
+  int s_min = 1;
+  if (l2_bytes > 0) {
+    const long long tile_bytes = 2ll * kTileN * kb_count * kBlockK * 2;
+    long long tiles_per = l2_bytes / tile_bytes;
+    if (tiles_per < 1) tiles_per = 1;
+    const long long s = (n_ct + tiles_per - 1) / tiles_per;
+    s_min = static_cast<int>(s > 64 ? 64 : s);
+  }
+  if (n_rt * s_min >= 2ll * sms) return s_min;
+  const int s_max = static_cast<int>(n_ct < 64 ? n_ct : 64);
+  int best_s = s_min;
   long long best_span = -1;
   std::vector<long long> load;
-  for (int s = 1; s <= s_max; ++s) {
+  for (int s = s_min; s <= s_max; ++s) {
     const long long items = n_rt * s;
     const int grid = static_cast<int>(items < sms ? items : sms);
     load.assign(grid, 0);
     for (long long it = 0; it < items; ++it) {
-      const long long sp = it % s;
+      const long long sp = it / n_rt;
       const long long tiles = n_ct * (sp + 1) / s - n_ct * sp / s;
       load[it % grid] += tiles + 1;   // +1: per-item fixed cost (row state, list write)
     }
@@ -334,11 +355,14 @@ using namespace amb;
 
 extern "C" {
 
-size_t amb_knn_ws_bytes(long long nrows, long long n, int k) {
+size_t amb_knn_ws_bytes(long long nrows, long long n, int d, int k) {
   const int Kt = pick_kt(k);
-  if (!Kt || nrows < 0 || n <= 0) return 0;
-  // worst-case split count is 32 (pick_split), independent of the device
-  return knn_ws(nullptr, nrows, Kt, 32).bytes;
+  if (!Kt || nrows < 0 || n <= 0 || d <= 0) return 0;
+  // upper bound of pick_split() without knowing the device: one split once there
+  // are clearly >= 2 row tiles per SM (up to 160 SMs), else the cap of 64
+  const long long n_rt = (nrows + kTileM - 1) / kTileM;
+  const int bound = n_rt >= 2ll * 160 ? 1 : 64;
+  return knn_ws(nullptr, nrows, Kt, bound).bytes;
 }
 
 int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long long ld, const void* packed,
@@ -361,7 +385,11 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
   PackedPtrs p = packed_ptrs(const_cast<void*>(packed), n, d);
   const long long n_rt = (nrows + kTileM - 1) / kTileM;
   const long long n_ct = p.rows_pad / kTileN;
-  const int n_split = pick_split(dev, n_rt, n_ct);
+  int n_split = pick_split(dev, n_rt, n_ct, p.kb_count, 0);
+  if (const char* e = getenv("AMB_TOPK_SPLIT")) {   // tuning knob
+    const int v = atoi(e);
+    if (v >= 1 && v <= 64 && v <= n_ct) n_split = v;
+  }
   KnnWs w = knn_ws(ws, nrows, Kt, n_split);
   if (!ws || ws_bytes < w.bytes) return set_error(AMB_ERR_WS, "amb_knn_radii: workspace %zu < %zu", ws_bytes, w.bytes);
   const long long list_rows = round_up_ll(nrows, kTileM);
@@ -479,7 +507,11 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   g.n_problems = 1;
   g.n_rt = static_cast<int>((nrows + kTileM - 1) / kTileM);
   g.n_ct = static_cast<int>(pc.rows_pad / kTileN);
-  g.n_split = pick_split(dev, g.n_rt, g.n_ct);
+  g.n_split = pick_split(dev, g.n_rt, g.n_ct, pc.kb_count, kCountSplitBytes);
+  if (const char* e = getenv("AMB_COUNT_SPLIT")) {   // tuning knob
+    const int v = atoi(e);
+    if (v >= 1 && v <= 64 && v <= g.n_ct) g.n_split = v;
+  }
   g.lbo_bytes = 128;
   g.sbo_bytes = 512;
   CountEpi epi{pr.inv_scale, pr.norm, a_lo, a_hi, pc.inv_scale, pc.norm, b_lo, b_hi, col_count, row_recall,

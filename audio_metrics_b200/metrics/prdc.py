@@ -32,7 +32,7 @@ def nearest_neighbour_distances(input_features, nearest_k, row_range=None):
     radii = torch.empty(nrows, dtype=torch.float32, device=dev)
     if nrows == 0:
         return radii
-    ws = _lib.workspace(L.amb_knn_ws_bytes(nrows, n, nearest_k), dev)
+    ws = _lib.workspace(L.amb_knn_ws_bytes(nrows, n, d, int(nearest_k)), dev)
     _lib.check(L.amb_knn_radii(dev.index, _lib.stream_ptr(dev), x.data_ptr(), _lib.dtype_code(x), x.stride(0),
                                c.packed().data_ptr(), n, d, row0, nrows, int(nearest_k), radii.data_ptr(),
                                ws.data_ptr(), ws.numel()))

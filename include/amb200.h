@@ -116,7 +116,7 @@ int amb_kd_subsets(int dev, amb_stream_t stream, const void* F1, long long n1, l
  * Computes radii for rows [row0, row0+nrows) of the set (row0 % 128 == 0)
  * against all n rows.  radii: [nrows] fp32.  1 <= k <= 29 and k+1 <= n (the
  * reference's kthvalue raises for k+1 > n). */
-size_t amb_knn_ws_bytes(long long nrows, long long n, int k);
+size_t amb_knn_ws_bytes(long long nrows, long long n, int d, int k);
 int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long long ld,
                   const void* packed, long long n, int d, long long row0, long long nrows, int k,
                   float* radii, void* ws, size_t ws_bytes);
