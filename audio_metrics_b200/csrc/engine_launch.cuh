@@ -15,12 +15,12 @@ int launch_engine(cudaStream_t stream, int dev, const EngineGeom& g, const Epi& 
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(pair_engine_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(kEngineSmemBytes));
+                                    static_cast<int>(engine_smem_bytes<Epi>()));
   });
   // the attribute is per device; set it again cheaply when several devices are in use
   if (attr_err == cudaSuccess)
     attr_err = cudaFuncSetAttribute(pair_engine_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(kEngineSmemBytes));
+                                    static_cast<int>(engine_smem_bytes<Epi>()));
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(pair_engine)");
   const long long items = static_cast<long long>(g.n_problems) * g.n_rt * g.n_split;
   if (items <= 0) return AMB_OK;
@@ -30,7 +30,34 @@ int launch_engine(cudaStream_t stream, int dev, const EngineGeom& g, const Epi& 
   const double exec_flops = static_cast<double>(g.n_problems) * g.n_rt * g.n_ct * (2.0 * kTileM * kTileN) *
                             (g.kb_count * static_cast<double>(kBlockK)) * 3.0;
   void* tok = profile_begin(stream);
-  pair_engine_kernel<Epi><<<grid, kEngineThreads, kEngineSmemBytes, stream>>>(g, epi);
+  pair_engine_kernel<Epi><<<grid, kEngineThreads, engine_smem_bytes<Epi>(), stream>>>(g, epi);
+  profile_end(tok, stream, alg_pairs, exec_flops);
+  return check_launch(what);
+}
+
+// Single-pass variant (pair_engine1_kernel): resident A panel + B ring sized to what is
+// left of the 227 KiB of shared memory.  Only for kb_count <= kMaxResidentKb.
+constexpr size_t kMaxDynSmem = 232448;
+template <class Epi>
+int launch_engine1(cudaStream_t stream, int dev, EngineGeom g, const Epi& epi, const char* what,
+                   double alg_pairs = 0.0) {
+  if (g.kb_count > kMaxResidentKb) return set_error(AMB_ERR_ARG, "%s: kb_count %d too large for the resident panel", what, g.kb_count);
+  const size_t fixed = size_t(g.kb_count) * kChunkBytes + sizeof(EngineSmem) + (Epi::kScratch ? kScratchBytes : 0);
+  int n_stages = static_cast<int>((kMaxDynSmem - fixed) / kStage1Bytes);
+  if (n_stages > kMaxStages) n_stages = kMaxStages;
+  g.n_stages = n_stages;
+  const size_t smem = fixed + size_t(n_stages) * kStage1Bytes;
+  cudaError_t attr_err = cudaFuncSetAttribute(pair_engine1_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(kMaxDynSmem));
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(pair_engine1)");
+  const long long items = static_cast<long long>(g.n_problems) * g.n_rt * g.n_split;
+  if (items <= 0) return AMB_OK;
+  const int sms = sm_count(dev);
+  const unsigned grid = static_cast<unsigned>(items < sms ? items : sms);
+  const double exec_flops = static_cast<double>(g.n_problems) * g.n_rt * g.n_ct * (2.0 * kTileM * kTileN) *
+                            (g.kb_count * static_cast<double>(kBlockK));
+  void* tok = profile_begin(stream);
+  pair_engine1_kernel<Epi><<<grid, kEngineThreads, smem, stream>>>(g, epi);
   profile_end(tok, stream, alg_pairs, exec_flops);
   return check_launch(what);
 }

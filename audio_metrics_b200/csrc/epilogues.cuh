@@ -14,6 +14,7 @@ constexpr float kInf = __builtin_huge_valf();
 // ----------------------------------------------------------------- debug dump
 struct DumpEpi {
   static constexpr int kColVecs = 1;
+  static constexpr bool kScratch = false;
   const float* inv_a;
   const float* inv_b;
   float* C;
@@ -52,6 +53,7 @@ struct DumpEpi {
 // warp writes one fp64 partial per work item: partial[item*4 + quarter].
 struct KdEpi {
   static constexpr int kColVecs = 1;
+  static constexpr bool kScratch = false;
   const float* inv_a;
   const float* inv_b;
   int kernel_type;
@@ -136,6 +138,16 @@ __host__ __device__ inline float band_key(float nrm_x, float nrm_y_max) {
   // bound on |t~ - t| for t = |y|^2 - 2<x,y>
   return 2.0f * kBandDot * sqrtf(nrm_x) * sqrtf(nrm_y_max) + kBandAbs * (nrm_x + nrm_y_max);
 }
+// Single-pass engine (hi planes only, pair_engine1_kernel): with x = hx + ex, y = hy + ey,
+//   <x,y> - <hx,hy> = <ex,hy> + <hx,ey> + <ex,ey>,   |.| <= (rho_x |y| + |x| rho_y)(1 + 2^-10)
+// where rho = |e| is the MEASURED residual norm of the row (pack.cu; <= 2^-11 |x|, typically
+// 0.4 of that), by Cauchy-Schwarz; the 32-step truncating accumulation adds at most
+// 2 * 32 * 2^-23 |x||y| (same model as above).  rho_y and |y| enter as set-wide maxima.
+constexpr float kBandAcc1 = 8.0e-6f;
+__host__ __device__ inline float band_key1(float nrm_x, float rho_x, float nrm_y_max, float rho_y_max) {
+  const float ax = sqrtf(nrm_x), ay = sqrtf(nrm_y_max);
+  return 2.0f * ((rho_x * ay + ax * rho_y_max) * 1.002f + kBandAcc1 * ax * ay) + kBandAbs * (nrm_x + nrm_y_max);
+}
 
 // -------------------------------------------------- per-row (k+1)-smallest lists
 // Ranking key for row i over columns j:  t_ij = |y_j|^2 - 2 <x_i, y_j>
@@ -147,6 +159,7 @@ __host__ __device__ inline float band_key(float nrm_x, float nrm_y_max) {
 template <int K>
 struct TopkEpi {
   static constexpr int kColVecs = 2;   // 0: inv_scale_b, 1: norm_b (+inf on padding)
+  static constexpr bool kScratch = true;
   const float* inv_a;
   const float* inv_b;
   const float* norm_b;
@@ -235,6 +248,7 @@ struct PairEntry { uint32_t i; uint32_t j_kind; };   // j_kind: bit 31 = 1 -> in
 
 struct CountEpi {
   static constexpr int kColVecs = 3;   // 0: inv_scale_b, 1: norm_b, 2: B_hi
+  static constexpr bool kScratch = false;
   const float* inv_a;
   const float* norm_a;
   const float* a_lo;       // indexed by packed A row

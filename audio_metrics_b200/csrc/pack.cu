@@ -38,7 +38,7 @@ pack_rows_kernel(const T* __restrict__ src, long long ld, int d, long long n_src
                  long long n_valid,               // rows >= n_valid (pre-gather index) are padding
                  long long row0, long long n_rows_out, __half* __restrict__ planes,
                  long long plane_halfs, int kb_count, float* __restrict__ inv_scale,
-                 float* __restrict__ norm) {
+                 float* __restrict__ norm, float* __restrict__ rho) {
   const int lane = threadIdx.x & 31;
   const int r = lane & 7, c = lane >> 3;
   const long long group = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -80,7 +80,7 @@ pack_rows_kernel(const T* __restrict__ src, long long ld, int d, long long n_src
   const double inv = ldexp(1.0, -sh);
 
   // pass 2: split, store, norm
-  double nrm = 0.0;
+  double nrm = 0.0, res = 0.0;
   const long long rb = out_row / kBlockRows;
   const int rin = static_cast<int>(out_row % kBlockRows);
   const long long chunk_row_off = ((static_cast<long long>(rin >> 3) * 4 + c) * 8 + (rin & 7)) * 8;
@@ -95,6 +95,8 @@ pack_rows_kernel(const T* __restrict__ src, long long ld, int d, long long n_src
       to_scaled_hi_lo<T>(v, scale, h[e], l[e]);
       const double xt = static_cast<double>(__half2float(h[e])) + static_cast<double>(__half2float(l[e]));
       nrm += xt * xt;
+      const double rm = static_cast<double>(v) * static_cast<double>(scale) - static_cast<double>(__half2float(h[e]));
+      res += rm * rm;   // exact remainder of the hi plane (fp64 product by a power of two is exact)
     }
     const long long off = (rb * kb_count + kb) * kChunkHalfs + chunk_row_off;
     *reinterpret_cast<uint4*>(planes + off) = *reinterpret_cast<const uint4*>(h);
@@ -102,13 +104,17 @@ pack_rows_kernel(const T* __restrict__ src, long long ld, int d, long long n_src
   }
   nrm += __shfl_xor_sync(0xffffffffu, nrm, 8);
   nrm += __shfl_xor_sync(0xffffffffu, nrm, 16);
+  res += __shfl_xor_sync(0xffffffffu, res, 8);
+  res += __shfl_xor_sync(0xffffffffu, res, 16);
   if (c == 0) {
     if (rowp) {
       inv_scale[out_row] = static_cast<float>(inv);
       norm[out_row] = static_cast<float>(nrm * inv * inv);
+      rho[out_row] = __double2float_ru(sqrt(res) * inv * (1.0 + 1e-7));
     } else {
       inv_scale[out_row] = 1.0f;
       norm[out_row] = __int_as_float(0x7f800000);  // +inf: padding row
+      rho[out_row] = 0.0f;
     }
   }
 }
@@ -116,7 +122,7 @@ pack_rows_kernel(const T* __restrict__ src, long long ld, int d, long long n_src
 int launch_pack(cudaStream_t stream, const void* src, int dtype, long long ld, int d,
                 long long n_src_rows, const int* gather, long long n_valid, long long row0,
                 long long n_rows_out, __half* planes, long long plane_halfs, int kb_count,
-                float* inv_scale, float* norm) {
+                float* inv_scale, float* norm, float* rho) {
   if (n_rows_out <= 0) return 0;
   const long long groups = n_rows_out / 8;
   const int threads = 256;
@@ -124,11 +130,11 @@ int launch_pack(cudaStream_t stream, const void* src, int dtype, long long ld, i
   if (dtype == AMB_F32) {
     pack_rows_kernel<float><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
         static_cast<const float*>(src), ld, d, n_src_rows, gather, n_valid, row0, n_rows_out,
-        planes, plane_halfs, kb_count, inv_scale, norm);
+        planes, plane_halfs, kb_count, inv_scale, norm, rho);
   } else if (dtype == AMB_F64) {
     pack_rows_kernel<double><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
         static_cast<const double*>(src), ld, d, n_src_rows, gather, n_valid, row0, n_rows_out,
-        planes, plane_halfs, kb_count, inv_scale, norm);
+        planes, plane_halfs, kb_count, inv_scale, norm, rho);
   } else {
     return set_error(AMB_ERR_ARG, "pack: dtype must be AMB_F32 or AMB_F64");
   }

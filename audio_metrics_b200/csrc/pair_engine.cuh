@@ -51,21 +51,30 @@ struct EngineGeom {
   // debug knobs (descriptor strides), normally 128 / 512
   uint32_t lbo_bytes;
   uint32_t sbo_bytes;
+  int n_stages;              // single-pass kernel: B ring depth chosen by the host (<= kMaxStages)
 };
 
+constexpr int kMaxStages = 8;
 struct EngineSmem {
   alignas(128) float colvec[2][kMaxColVecs][kTileN];   // bulk-copy destinations: keep 16 B aligned
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t cv_full[2];
+  uint64_t a_full;      // single-pass kernel: resident A panel landed
+  uint64_t a_empty;     //                     ... and is no longer read by any MMA
   uint32_t tmem_base;
   uint32_t pad_;
-  float scratch[kEpiThreads][33];   // per-row spill area for epilogues (stride 33: conflict-free)
 };
 
-constexpr size_t kEngineSmemBytes = size_t(kStages) * kStageBytes + sizeof(EngineSmem);
+// Epilogues that need it (Epi::kScratch) get 33 floats of shared memory per tile row
+// (stride 33: conflict-free), placed after EngineSmem.
+constexpr size_t kScratchBytes = size_t(kEpiThreads) * 33 * sizeof(float);
+template <class Epi>
+constexpr size_t engine_smem_bytes() {
+  return size_t(kStages) * kStageBytes + sizeof(EngineSmem) + (Epi::kScratch ? kScratchBytes : 0);
+}
 
 struct ItemCoord {
   int problem, rt, split, ct_begin, ct_end;
@@ -91,14 +100,58 @@ __device__ __forceinline__ ItemCoord decode_item(const EngineGeom& g, int item) 
 // Epilogue concept:
 //   struct Epi {
 //     static constexpr int kColVecs;                 // column vectors staged per tile
+//     static constexpr bool kScratch;                // wants the per-row scratch area
 //     struct Row;                                    // per-thread (= per tile row) state
 //     const float* colvec_ptr(int v) const;          // global array, indexed by packed B row
 //     void row_begin(Row&, const ItemCoord&, long long a_row /*packed A row*/) const;
 //     void chunk(Row&, const uint32_t (&acc)[32], const float (*cv)[kTileN], int col_in_tile,
 //                int col_in_problem, long long b_row0 /*packed B row of chunk column 0*/,
-//                float* scratch /*33 floats of shared memory private to this row*/) const;
+//                float* scratch /*33 floats private to this row, or nullptr*/) const;
 //     void row_end(Row&, const ItemCoord&, int item, long long a_row, int quarter, int lane) const;
 //   };
+
+// Epilogue role, shared by both kernels: warps 2..5, one TMEM lane quarter each.
+template <class Epi>
+__device__ __forceinline__ void epilogue_role(const EngineGeom& g, const Epi& epi, EngineSmem* sh,
+                                              uint32_t tmem_base, int warp, int lane) {
+  float* scratch = Epi::kScratch
+                       ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + sizeof(EngineSmem)) +
+                             (threadIdx.x - 64) * 33
+                       : nullptr;
+  const int n_items = g.n_problems * g.n_rt * g.n_split;
+  const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
+  const int row_in_tile = quarter * 32 + lane;
+  int acc = 0;
+  uint32_t acc_ph = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const ItemCoord c = decode_item(g, item);
+    const long long a_row = ((g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + c.rt) * static_cast<long long>(kTileM) + row_in_tile;
+    const long long b_row_base = static_cast<long long>((g.b_rb0 ? g.b_rb0[c.problem] : 0) + g.b_rb_base) * kBlockRows;
+    typename Epi::Row row;
+    epi.row_begin(row, c, a_row);
+    for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
+      const long long b_row0 = b_row_base + static_cast<long long>(ct) * kTileN;
+      mbar_wait(&sh->cv_full[acc], acc_ph);     // column vectors landed (producer bulk copy)
+      mbar_wait(&sh->tmem_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc) * kTileN +
+                              (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < kTileN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_addr + c0, r);
+        tmem_wait_ld();
+        epi.chunk(row, r, sh->colvec[acc], c0, ct * kTileN + c0, b_row0 + c0, scratch);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1;
+    }
+    epi.row_end(row, c, item, a_row, quarter, lane);
+  }
+}
 
 template <class Epi>
 __global__ void __launch_bounds__(kEngineThreads, 1)
@@ -217,40 +270,149 @@ pair_engine_kernel(const EngineGeom g, const Epi epi) {
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue
-    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
-    const int row_in_tile = quarter * 32 + lane;
-    const int epi_tid = threadIdx.x - 64;         // 0..127
-    int acc = 0;
-    uint32_t acc_ph = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const ItemCoord c = decode_item(g, item);
-      const long long a_row = ((g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + c.rt) * static_cast<long long>(kTileM) + row_in_tile;
-      const long long b_row_base = static_cast<long long>((g.b_rb0 ? g.b_rb0[c.problem] : 0) + g.b_rb_base) * kBlockRows;
-      typename Epi::Row row;
-      epi.row_begin(row, c, a_row);
-      for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
-        const long long b_row0 = b_row_base + static_cast<long long>(ct) * kTileN;
-        mbar_wait(&sh->cv_full[acc], acc_ph);     // column vectors landed (producer bulk copy)
-        mbar_wait(&sh->tmem_full[acc], acc_ph);
-        tc_fence_after();
-        const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc) * kTileN +
-                                (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < kTileN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_addr + c0, r);
-          tmem_wait_ld();
-          epi.chunk(row, r, sh->colvec[acc], c0, ct * kTileN + c0, b_row0 + c0, sh->scratch[epi_tid]);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_ph ^= 1;
-      }
-      epi.row_end(row, c, item, a_row, quarter, lane);
+    epilogue_role(g, epi, sh, tmem_base, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// Single-pass variant (radii and counts): one fp16 MMA per product on the hi
+// plane only.  The result is only a filter — every decision inside its (wider)
+// error band is re-made exactly by the refine kernels — so the tensor cores do a
+// third of the work.  With a third of the math per byte the operand traffic would
+// out-run L2 (A + B re-read per tile = 94 B/clk/SM), so the A row panel of the
+// item (128 rows x kpad fp16 <= 128 KiB) stays RESIDENT in shared memory for the
+// whole column sweep and only B streams through an n_stages-deep ring of 16 KiB
+// stages.  Requires kb_count <= 16 (d <= 512); wider inputs use the 3-pass kernel.
+constexpr int kStage1Bytes = 2 * kChunkBytes;            // B hi, two row blocks
+constexpr int kMaxResidentKb = 16;
+
+template <class Epi>
+__global__ void __launch_bounds__(kEngineThreads, 1)
+pair_engine1_kernel(const EngineGeom g, const Epi epi) {
+  extern __shared__ __align__(1024) uint8_t smem_buf[];
+  uint8_t* a_panel = smem_buf;                                           // kb_count chunks
+  uint8_t* stage_base = smem_buf + size_t(g.kb_count) * kChunkBytes;
+  EngineSmem* sh = reinterpret_cast<EngineSmem*>(stage_base + size_t(g.n_stages) * kStage1Bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_items = g.n_problems * g.n_rt * g.n_split;
+  const int n_stages = g.n_stages;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&sh->full[s], 1);
+      mbar_init(&sh->empty[s], 1);
     }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&sh->tmem_full[a], 1);
+      mbar_init(&sh->tmem_empty[a], 4);
+      mbar_init(&sh->cv_full[a], 1);
+    }
+    mbar_init(&sh->a_full, 1);
+    mbar_init(&sh->a_empty, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&sh->tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0, a_ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(g, item);
+        const long long a_rb = (g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + c.rt;
+        const long long b_rb_base = (g.b_rb0 ? g.b_rb0[c.problem] : 0) + g.b_rb_base;
+        const __half* a_src = g.a_planes + a_rb * g.kb_count * kChunkHalfs;
+        // resident A panel: one contiguous kb_count * 8 KiB run of the hi plane
+        mbar_wait(&sh->a_empty, a_ph ^ 1);
+        mbar_expect_tx(&sh->a_full, static_cast<uint32_t>(g.kb_count) * kChunkBytes);
+        for (int kb = 0; kb < g.kb_count; ++kb)
+          bulk_g2s(a_panel + size_t(kb) * kChunkBytes, a_src + static_cast<long long>(kb) * kChunkHalfs, kChunkBytes,
+                   &sh->a_full);
+        a_ph ^= 1;
+        for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
+          const __half* b_src = g.b_planes + (b_rb_base + 2ll * ct) * g.kb_count * kChunkHalfs;
+          const long long b_next = static_cast<long long>(g.kb_count) * kChunkHalfs;
+          mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+          mbar_expect_tx(&sh->cv_full[acc], Epi::kColVecs * kTileN * 4);
+#pragma unroll
+          for (int v = 0; v < Epi::kColVecs; ++v)
+            bulk_g2s(sh->colvec[acc][v], epi.colvec_ptr(v) + (b_rb_base + 2ll * ct) * kBlockRows, kTileN * 4,
+                     &sh->cv_full[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_ph ^= 1;
+          for (int kb = 0; kb < g.kb_count; ++kb) {
+            mbar_wait(&sh->empty[s], ph ^ 1);
+            uint8_t* st = stage_base + size_t(s) * kStage1Bytes;
+            mbar_expect_tx(&sh->full[s], kStage1Bytes);
+            const long long ko = static_cast<long long>(kb) * kChunkHalfs;
+            bulk_g2s(st, b_src + ko, kChunkBytes, &sh->full[s]);
+            bulk_g2s(st + kChunkBytes, b_src + b_next + ko, kChunkBytes, &sh->full[s]);
+            if (++s == n_stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kTileM, kTileN);
+      const uint32_t a_base = smem_u32(a_panel);
+      int s = 0;
+      uint32_t ph = 0, a_ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(g, item);
+        mbar_wait(&sh->a_full, a_ph);
+        a_ph ^= 1;
+        for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
+          mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kTileN;
+          for (int kb = 0; kb < g.kb_count; ++kb) {
+            mbar_wait(&sh->full[s], ph);
+            tc_fence_after();
+            const uint32_t st = smem_u32(stage_base + size_t(s) * kStage1Bytes);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint32_t koff = ks * 256;
+              const uint64_t a_hi = make_kmajor_desc(a_base + kb * kChunkBytes + koff, g.lbo_bytes, g.sbo_bytes);
+              const uint64_t b_hi = make_kmajor_desc(st + koff, g.lbo_bytes, g.sbo_bytes);
+              mma_f16_ss(d_tmem, a_hi, b_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+            }
+            tc_commit(&sh->empty[s]);
+            if (++s == n_stages) { s = 0; ph ^= 1; }
+          }
+          tc_commit(&sh->tmem_full[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_ph ^= 1;
+        }
+        tc_commit(&sh->a_empty);   // all MMAs that read this A panel are done
+      }
+    }
+  } else {
+    epilogue_role(g, epi, sh, tmem_base, warp, lane);
   }
 
   tc_fence_before();

@@ -11,16 +11,29 @@
 namespace amb {
 
 // ------------------------------------------------------------------ helpers
-__global__ void max_norm_kernel(const float* __restrict__ norm, long long n, float* out_max) {
-  float m = 0.f;
+// out_max[0] = max |x|^2, out_max[1] = max rho over the real rows of a packed set.
+__global__ void max_norm_kernel(const float* __restrict__ norm, const float* __restrict__ rho, long long n,
+                                float* out_max) {
+  float m = 0.f, mr = 0.f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float v = norm[i];
-    if (v < kInf) m = fmaxf(m, v);
+    if (v < kInf) { m = fmaxf(m, v); mr = fmaxf(mr, rho[i]); }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out_max), __float_as_int(m));  // m >= 0
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+  }
+  if ((threadIdx.x & 31) == 0) {   // values are >= 0: integer order == float order
+    atomicMax(reinterpret_cast<int*>(out_max), __float_as_int(m));
+    atomicMax(reinterpret_cast<int*>(out_max) + 1, __float_as_int(mr));
+  }
+}
+
+// Error band of the filter pass for row x against a set with maxima mx = {max |y|^2, max rho_y}.
+__device__ __forceinline__ float filter_band(bool single_pass, float nx, float rho_x, const float* mx) {
+  return single_pass ? band_key1(nx, rho_x, mx[0], mx[1]) : band_key(nx, mx[0]);
 }
 
 template <typename T>
@@ -50,8 +63,9 @@ __global__ void __launch_bounds__(256)
 knn_refine_kernel(const T* __restrict__ X, long long ld, int d, long long n, long long row0,
                   long long nrows, int k, int Kt, int n_split, long long list_rows,
                   const float* __restrict__ keys, const int* __restrict__ cols,
-                  const float* __restrict__ norm, const float* __restrict__ max_norm,
-                  float* __restrict__ radii, int* __restrict__ unresolved, int* __restrict__ n_unresolved) {
+                  const float* __restrict__ norm, const float* __restrict__ rho, bool single_pass,
+                  const float* __restrict__ max_norm, float* __restrict__ radii, int* __restrict__ unresolved,
+                  int* __restrict__ n_unresolved) {
   const int lane = threadIdx.x & 31;
   const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   if (row >= nrows) return;
@@ -113,7 +127,7 @@ knn_refine_kernel(const T* __restrict__ X, long long ld, int d, long long n, lon
   const int last_sel = __shfl_sync(0xffffffffu, sel_col, Kt - 1);
   if (ok && last_sel >= 0) {
     const float nx = norm[i];
-    const float band = band_key(nx, *max_norm);
+    const float band = filter_band(single_pass, nx, rho[i], max_norm);
     const double bound = static_cast<double>(nx) + static_cast<double>(t_last) - static_cast<double>(band);
     if (!(r2 < bound)) ok = false;
   }
@@ -184,7 +198,8 @@ knn_bruteforce_kernel(const T* __restrict__ X, long long ld, int d, long long n,
 }
 
 // ---------------------------------------------------------- counts: thresholds
-__global__ void prdc_thresholds_kernel(const float* __restrict__ norm, const float* __restrict__ radii,
+__global__ void prdc_thresholds_kernel(const float* __restrict__ norm, const float* __restrict__ rho,
+                                       bool single_pass, const float* __restrict__ radii,
                                        long long n_valid, long long rows_pad,
                                        const float* __restrict__ other_max_norm, float* __restrict__ lo,
                                        float* __restrict__ hi) {
@@ -196,7 +211,7 @@ __global__ void prdc_thresholds_kernel(const float* __restrict__ norm, const flo
   const float r2 = r * r;
   // band on the key plus slack for the fp32 rounding of r^2, |x|^2 and of the
   // final fp32 distance the refine kernel compares (3e-7 ~ 2.5 ulp)
-  const float band = band_key(nx, *other_max_norm) + 3e-7f * (r2 + nx);
+  const float band = filter_band(single_pass, nx, rho[i], other_max_norm) + 3e-7f * (r2 + nx);
   const float a = r2 - nx;
   lo[i] = a - band;
   hi[i] = a + band;
@@ -344,9 +359,18 @@ static KnnWs knn_ws(void* ws, long long nrows, int Kt, int n_split) {
 
 template <int K>
 static int run_topk(cudaStream_t st, int dev, EngineGeom& g, const PackedPtrs& p, const KnnWs& w,
-                    long long list_rows, long long a_row_base, double alg_pairs) {
+                    long long list_rows, long long a_row_base, double alg_pairs, bool single_pass) {
   TopkEpi<K> epi{p.inv_scale, p.inv_scale, p.norm, w.keys, w.cols, list_rows, a_row_base};
+  if (single_pass) return launch_engine1(st, dev, g, epi, "pair_engine1<topk>", alg_pairs);
   return launch_engine(st, dev, g, epi, "pair_engine<topk>", alg_pairs);
+}
+
+// The filter runs as ONE fp16 MMA per product (hi planes) whenever the A row panel fits
+// in shared memory (d <= 512); AMB_PASSES=3 forces the three-MMA split-precision sweep.
+static bool use_single_pass(int kb_count) {
+  if (kb_count > kMaxResidentKb) return false;
+  const char* e = getenv("AMB_PASSES");
+  return !(e && atoi(e) == 3);
 }
 
 }  // namespace amb
@@ -395,8 +419,9 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
   const long long list_rows = round_up_ll(nrows, kTileM);
   int rc = check_cuda(cudaMemsetAsync(w.n_unresolved, 0, 512, st), "memset");   // n_unresolved + max_norm
   if (rc) return rc;
-  max_norm_kernel<<<64, 256, 0, st>>>(p.norm, p.rows_pad, w.max_norm);
+  max_norm_kernel<<<64, 256, 0, st>>>(p.norm, p.rho, p.rows_pad, w.max_norm);
   if ((rc = check_launch("max_norm_kernel"))) return rc;
+  const bool sp = use_single_pass(p.kb_count);
 
   EngineGeom g{};
   g.a_planes = p.planes;
@@ -411,9 +436,9 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
   g.n_split = n_split;
   g.lbo_bytes = 128;
   g.sbo_bytes = 512;
-  if (Kt == 8) rc = run_topk<8>(st, dev, g, p, w, list_rows, row0, static_cast<double>(nrows) * n);
-  else if (Kt == 16) rc = run_topk<16>(st, dev, g, p, w, list_rows, row0, static_cast<double>(nrows) * n);
-  else rc = run_topk<32>(st, dev, g, p, w, list_rows, row0, static_cast<double>(nrows) * n);
+  if (Kt == 8) rc = run_topk<8>(st, dev, g, p, w, list_rows, row0, static_cast<double>(nrows) * n, sp);
+  else if (Kt == 16) rc = run_topk<16>(st, dev, g, p, w, list_rows, row0, static_cast<double>(nrows) * n, sp);
+  else rc = run_topk<32>(st, dev, g, p, w, list_rows, row0, static_cast<double>(nrows) * n, sp);
   if (rc) return rc;
 
   const unsigned blocks = static_cast<unsigned>((nrows * 32 + 255) / 256);
@@ -424,14 +449,16 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
   if (dtype == AMB_F32) {
     const float* Xf = static_cast<const float*>(X);
     knn_refine_kernel<float><<<blocks, 256, 0, st>>>(Xf, ld, d, n, row0, nrows, k, Kt, n_split, list_rows, w.keys,
-                                                     w.cols, p.norm, w.max_norm, radii, w.unresolved, w.n_unresolved);
+                                                     w.cols, p.norm, p.rho, sp, w.max_norm, radii, w.unresolved,
+                                                     w.n_unresolved);
     if ((rc = check_launch("knn_refine_kernel"))) return rc;
     knn_bruteforce_kernel<float><<<bf_blocks, 256, 0, st>>>(Xf, ld, d, n, row0, k, w.unresolved, w.n_unresolved,
                                                             static_cast<int>(max_rows), radii);
   } else {
     const double* Xd = static_cast<const double*>(X);
     knn_refine_kernel<double><<<blocks, 256, 0, st>>>(Xd, ld, d, n, row0, nrows, k, Kt, n_split, list_rows, w.keys,
-                                                      w.cols, p.norm, w.max_norm, radii, w.unresolved, w.n_unresolved);
+                                                      w.cols, p.norm, p.rho, sp, w.max_norm, radii, w.unresolved,
+                                                      w.n_unresolved);
     if ((rc = check_launch("knn_refine_kernel"))) return rc;
     knn_bruteforce_kernel<double><<<bf_blocks, 256, 0, st>>>(Xd, ld, d, n, row0, k, w.unresolved, w.n_unresolved,
                                                              static_cast<int>(max_rows), radii);
@@ -486,15 +513,16 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   if ((rc = check_cuda(cudaMemsetAsync(q, 0, 512, st), "memset"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(row_recall, 0, nrows, st), "memset"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(row_cover, 0, nrows, st), "memset"))) return rc;
-  max_norm_kernel<<<64, 256, 0, st>>>(pr.norm, pr.rows_pad, max_ref);
+  const bool sp = use_single_pass(pr.kb_count);
+  max_norm_kernel<<<64, 256, 0, st>>>(pr.norm, pr.rho, pr.rows_pad, max_ref);
   if ((rc = check_launch("max_norm_kernel"))) return rc;
-  max_norm_kernel<<<64, 256, 0, st>>>(pc.norm, pc.rows_pad, max_cand);
+  max_norm_kernel<<<64, 256, 0, st>>>(pc.norm, pc.rho, pc.rows_pad, max_cand);
   if ((rc = check_launch("max_norm_kernel"))) return rc;
   prdc_thresholds_kernel<<<static_cast<unsigned>((pr.rows_pad + 255) / 256), 256, 0, st>>>(
-      pr.norm, r_ref, n_ref, pr.rows_pad, max_cand, a_lo, a_hi);
+      pr.norm, pr.rho, sp, r_ref, n_ref, pr.rows_pad, max_cand, a_lo, a_hi);
   if ((rc = check_launch("prdc_thresholds_kernel"))) return rc;
   prdc_thresholds_kernel<<<static_cast<unsigned>((pc.rows_pad + 255) / 256), 256, 0, st>>>(
-      pc.norm, r_cand, m, pc.rows_pad, max_ref, b_lo, b_hi);
+      pc.norm, pc.rho, sp, r_cand, m, pc.rows_pad, max_ref, b_lo, b_hi);
   if ((rc = check_launch("prdc_thresholds_kernel"))) return rc;
 
   EngineGeom g{};
@@ -507,7 +535,8 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   g.n_problems = 1;
   g.n_rt = static_cast<int>((nrows + kTileM - 1) / kTileM);
   g.n_ct = static_cast<int>(pc.rows_pad / kTileN);
-  g.n_split = pick_split(dev, g.n_rt, g.n_ct, pc.kb_count, kCountSplitBytes);
+  // the single-pass kernel keeps the A panel in shared memory: no L2 pressure from A, one split
+  g.n_split = pick_split(dev, g.n_rt, g.n_ct, pc.kb_count, sp ? 0 : kCountSplitBytes);
   if (const char* e = getenv("AMB_COUNT_SPLIT")) {   // tuning knob
     const int v = atoi(e);
     if (v >= 1 && v <= 64 && v <= g.n_ct) g.n_split = v;
@@ -516,7 +545,9 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   g.sbo_bytes = 512;
   CountEpi epi{pr.inv_scale, pr.norm, a_lo, a_hi, pc.inv_scale, pc.norm, b_lo, b_hi, col_count, row_recall,
                row_cover, row0, row0 + nrows, list, list_count, static_cast<unsigned long long>(cap)};
-  if ((rc = launch_engine(st, dev, g, epi, "pair_engine<count>", static_cast<double>(nrows) * m))) return rc;
+  rc = sp ? launch_engine1(st, dev, g, epi, "pair_engine1<count>", static_cast<double>(nrows) * m)
+          : launch_engine(st, dev, g, epi, "pair_engine<count>", static_cast<double>(nrows) * m);
+  if (rc) return rc;
 
   const int blocks = 8 * sm_count(dev);
   if (dtype == AMB_F32)
