@@ -201,7 +201,13 @@ int amb_debug_dot_matrix(int dev, amb_stream_t stream, const void* packed_a, lon
   g.lbo_bytes = lbo ? lbo : 128;
   g.sbo_bytes = sbo ? sbo : 512;
   DumpEpi epi{a.inv_scale, b.inv_scale, C, ldc, na, nb, ldc == 0 ? 1 : 0};
-  return launch_engine(static_cast<cudaStream_t>(stream), dev, g, epi, "pair_engine<dump>");
+  // AMB_DEBUG_SINGLE=1: hi planes only through the single-pass kernel (11-bit operands)
+  const char* e = getenv("AMB_DEBUG_SINGLE");
+  if (e && atoi(e) == 1 && g.kb_count <= kMaxResidentKb)
+    return launch_engine1(static_cast<cudaStream_t>(stream), dev, g, epi, "pair_engine1<dump>",
+                          static_cast<double>(na) * nb);
+  return launch_engine(static_cast<cudaStream_t>(stream), dev, g, epi, "pair_engine<dump>",
+                       static_cast<double>(na) * nb);
 }
 
 }  // extern "C"

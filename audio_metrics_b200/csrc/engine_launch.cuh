@@ -1,6 +1,7 @@
 // Host-side launcher for the pair engine; include in the .cu that instantiates
 // a given epilogue.
 #pragma once
+#include <cstdlib>
 #include <mutex>
 
 #include "epilogues.cuh"
@@ -45,6 +46,10 @@ int launch_engine1(cudaStream_t stream, int dev, EngineGeom g, const Epi& epi, c
   const size_t fixed = size_t(g.kb_count) * kChunkBytes + sizeof(EngineSmem) + (Epi::kScratch ? kScratchBytes : 0);
   int n_stages = static_cast<int>((kMaxDynSmem - fixed) / kStage1Bytes);
   if (n_stages > kMaxStages) n_stages = kMaxStages;
+  if (const char* e = getenv("AMB_STAGES")) {   // tuning knob: shallower B ring
+    const int v = atoi(e);
+    if (v >= 2 && v < n_stages) n_stages = v;
+  }
   g.n_stages = n_stages;
   const size_t smem = fixed + size_t(n_stages) * kStage1Bytes;
   cudaError_t attr_err = cudaFuncSetAttribute(pair_engine1_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,

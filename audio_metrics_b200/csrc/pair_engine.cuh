@@ -189,33 +189,36 @@ pair_engine_kernel(const EngineGeom g, const Epi epi) {
 
   if (warp == 0) {
     // ------------------------------------------------------------ producer
-    if (lane == 0) {
-      // the A row panel is re-read for every column tile of the item: ask L2 to keep it
-      const uint64_t keep = l2_policy_evict_last();
-      int s = 0;
-      uint32_t ph = 0;
-      int acc = 0;
-      uint32_t acc_ph = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const ItemCoord c = decode_item(g, item);
-        const long long a_rb = (g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + c.rt;
-        const long long b_rb_base = (g.b_rb0 ? g.b_rb0[c.problem] : 0) + g.b_rb_base;
-        const __half* a_src = g.a_planes + a_rb * g.kb_count * kChunkHalfs;
-        for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
-          const __half* b_src = g.b_planes + (b_rb_base + 2ll * ct) * g.kb_count * kChunkHalfs;
-          const long long b_next = static_cast<long long>(g.kb_count) * kChunkHalfs;
-          // this tile's column vectors ride the same engine: 1 KiB bulk copies into
-          // the buffer the epilogue released two tiles ago
-          mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+    // (whole warp runs the loops; one elected lane issues — see elect_one())
+    // the A row panel is re-read for every column tile of the item: ask L2 to keep it
+    const uint64_t keep = l2_policy_evict_last();
+    int s = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item(g, item);
+      const long long a_rb = (g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + c.rt;
+      const long long b_rb_base = (g.b_rb0 ? g.b_rb0[c.problem] : 0) + g.b_rb_base;
+      const __half* a_src = g.a_planes + a_rb * g.kb_count * kChunkHalfs;
+      for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
+        const __half* b_src = g.b_planes + (b_rb_base + 2ll * ct) * g.kb_count * kChunkHalfs;
+        const long long b_next = static_cast<long long>(g.kb_count) * kChunkHalfs;
+        // this tile's column vectors ride the same engine: 1 KiB bulk copies into
+        // the buffer the epilogue released two tiles ago
+        mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&sh->cv_full[acc], Epi::kColVecs * kTileN * 4);
 #pragma unroll
           for (int v = 0; v < Epi::kColVecs; ++v)
             bulk_g2s(sh->colvec[acc][v], epi.colvec_ptr(v) + (b_rb_base + 2ll * ct) * kBlockRows, kTileN * 4,
                      &sh->cv_full[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_ph ^= 1;
-          for (int kb = 0; kb < g.kb_count; ++kb) {
-            mbar_wait(&sh->empty[s], ph ^ 1);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
+        for (int kb = 0; kb < g.kb_count; ++kb) {
+          mbar_wait(&sh->empty[s], ph ^ 1);
+          if (elect_one()) {
             uint8_t* st = stage_base + size_t(s) * kStageBytes;
             mbar_expect_tx(&sh->full[s], kStageBytes);
             const long long ko = static_cast<long long>(kb) * kChunkHalfs;
@@ -224,51 +227,52 @@ pair_engine_kernel(const EngineGeom g, const Epi epi) {
             bulk_g2s(st + 2 * kChunkBytes, b_src + ko, kChunkBytes, &sh->full[s]);
             bulk_g2s(st + 3 * kChunkBytes, b_src + b_next + ko, kChunkBytes, &sh->full[s]);
             bulk_g2s(st + 4 * kChunkBytes, b_src + g.b_plane_halfs + ko, kChunkBytes, &sh->full[s]);
-            bulk_g2s(st + 5 * kChunkBytes, b_src + g.b_plane_halfs + b_next + ko, kChunkBytes,
-                     &sh->full[s]);
-            if (++s == kStages) { s = 0; ph ^= 1; }
+            bulk_g2s(st + 5 * kChunkBytes, b_src + g.b_plane_halfs + b_next + ko, kChunkBytes, &sh->full[s]);
           }
+          if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(kTileM, kTileN);
-      int s = 0;
-      uint32_t ph = 0;
-      int acc = 0;
-      uint32_t acc_ph = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const ItemCoord c = decode_item(g, item);
-        for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
-          mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+    constexpr uint32_t idesc = make_idesc_f16(kTileM, kTileN);
+    const uint64_t desc0 = make_kmajor_desc(smem_u32(stage_base), g.lbo_bytes, g.sbo_bytes);
+    int s = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item(g, item);
+      for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
+        mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kTileN;
+        for (int kb = 0; kb < g.kb_count; ++kb) {
+          mbar_wait(&sh->full[s], ph);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kTileN;
-          for (int kb = 0; kb < g.kb_count; ++kb) {
-            mbar_wait(&sh->full[s], ph);
-            tc_fence_after();
-            const uint32_t st = smem_u32(stage_base + size_t(s) * kStageBytes);
+          if (elect_one()) {
+            // descriptor address field counts 16-byte units: stage s at +s*kStageBytes/16
+            const uint64_t st = desc0 + static_cast<uint64_t>(s * (kStageBytes >> 4));
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint32_t koff = ks * 256;   // two 8-wide k chunks of 128 B
-              const uint64_t a_hi = make_kmajor_desc(st + 0 * kChunkBytes + koff, g.lbo_bytes, g.sbo_bytes);
-              const uint64_t a_lo = make_kmajor_desc(st + 1 * kChunkBytes + koff, g.lbo_bytes, g.sbo_bytes);
-              const uint64_t b_hi = make_kmajor_desc(st + 2 * kChunkBytes + koff, g.lbo_bytes, g.sbo_bytes);
-              const uint64_t b_lo = make_kmajor_desc(st + 4 * kChunkBytes + koff, g.lbo_bytes, g.sbo_bytes);
+              const uint64_t a_hi = st + (0 * kChunkBytes + ks * 256) / 16;   // two 8-wide k chunks of 128 B
+              const uint64_t a_lo = st + (1 * kChunkBytes + ks * 256) / 16;
+              const uint64_t b_hi = st + (2 * kChunkBytes + ks * 256) / 16;
+              const uint64_t b_lo = st + (4 * kChunkBytes + ks * 256) / 16;
               mma_f16_ss(d_tmem, a_hi, b_lo, idesc, (kb | ks) != 0 ? 1u : 0u);
               mma_f16_ss(d_tmem, a_lo, b_hi, idesc, 1u);
               mma_f16_ss(d_tmem, a_hi, b_hi, idesc, 1u);
             }
             tc_commit(&sh->empty[s]);
-            if (++s == kStages) { s = 0; ph ^= 1; }
           }
-          tc_commit(&sh->tmem_full[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_ph ^= 1;
+          if (++s == kStages) { s = 0; ph ^= 1; }
         }
+        if (elect_one()) tc_commit(&sh->tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
       }
     }
+    __syncwarp();
   } else {
     epilogue_role(g, epi, sh, tmem_base, warp, lane);
   }
@@ -333,84 +337,87 @@ pair_engine1_kernel(const EngineGeom g, const Epi epi) {
 
   if (warp == 0) {
     // ------------------------------------------------------------ producer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0, a_ph = 0;
-      int acc = 0;
-      uint32_t acc_ph = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const ItemCoord c = decode_item(g, item);
-        const long long a_rb = (g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + c.rt;
-        const long long b_rb_base = (g.b_rb0 ? g.b_rb0[c.problem] : 0) + g.b_rb_base;
-        const __half* a_src = g.a_planes + a_rb * g.kb_count * kChunkHalfs;
-        // resident A panel: one contiguous kb_count * 8 KiB run of the hi plane
-        mbar_wait(&sh->a_empty, a_ph ^ 1);
+    int s = 0;
+    uint32_t ph = 0, a_ph = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item(g, item);
+      const long long a_rb = (g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + c.rt;
+      const long long b_rb_base = (g.b_rb0 ? g.b_rb0[c.problem] : 0) + g.b_rb_base;
+      const __half* a_src = g.a_planes + a_rb * g.kb_count * kChunkHalfs;
+      // resident A panel: one contiguous kb_count * 8 KiB run of the hi plane
+      mbar_wait(&sh->a_empty, a_ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&sh->a_full, static_cast<uint32_t>(g.kb_count) * kChunkBytes);
         for (int kb = 0; kb < g.kb_count; ++kb)
           bulk_g2s(a_panel + size_t(kb) * kChunkBytes, a_src + static_cast<long long>(kb) * kChunkHalfs, kChunkBytes,
                    &sh->a_full);
-        a_ph ^= 1;
-        for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
-          const __half* b_src = g.b_planes + (b_rb_base + 2ll * ct) * g.kb_count * kChunkHalfs;
-          const long long b_next = static_cast<long long>(g.kb_count) * kChunkHalfs;
-          mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+      }
+      a_ph ^= 1;
+      for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
+        const __half* b_src = g.b_planes + (b_rb_base + 2ll * ct) * g.kb_count * kChunkHalfs;
+        const long long b_next = static_cast<long long>(g.kb_count) * kChunkHalfs;
+        mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&sh->cv_full[acc], Epi::kColVecs * kTileN * 4);
 #pragma unroll
           for (int v = 0; v < Epi::kColVecs; ++v)
             bulk_g2s(sh->colvec[acc][v], epi.colvec_ptr(v) + (b_rb_base + 2ll * ct) * kBlockRows, kTileN * 4,
                      &sh->cv_full[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_ph ^= 1;
-          for (int kb = 0; kb < g.kb_count; ++kb) {
-            mbar_wait(&sh->empty[s], ph ^ 1);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
+        for (int kb = 0; kb < g.kb_count; ++kb) {
+          mbar_wait(&sh->empty[s], ph ^ 1);
+          if (elect_one()) {
             uint8_t* st = stage_base + size_t(s) * kStage1Bytes;
             mbar_expect_tx(&sh->full[s], kStage1Bytes);
             const long long ko = static_cast<long long>(kb) * kChunkHalfs;
             bulk_g2s(st, b_src + ko, kChunkBytes, &sh->full[s]);
             bulk_g2s(st + kChunkBytes, b_src + b_next + ko, kChunkBytes, &sh->full[s]);
-            if (++s == n_stages) { s = 0; ph ^= 1; }
           }
+          if (++s == n_stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(kTileM, kTileN);
-      const uint32_t a_base = smem_u32(a_panel);
-      int s = 0;
-      uint32_t ph = 0, a_ph = 0;
-      int acc = 0;
-      uint32_t acc_ph = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const ItemCoord c = decode_item(g, item);
-        mbar_wait(&sh->a_full, a_ph);
-        a_ph ^= 1;
-        for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
-          mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+    constexpr uint32_t idesc = make_idesc_f16(kTileM, kTileN);
+    const uint64_t a_desc0 = make_kmajor_desc(smem_u32(a_panel), g.lbo_bytes, g.sbo_bytes);
+    const uint64_t b_desc0 = make_kmajor_desc(smem_u32(stage_base), g.lbo_bytes, g.sbo_bytes);
+    int s = 0;
+    uint32_t ph = 0, a_ph = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item(g, item);
+      mbar_wait(&sh->a_full, a_ph);
+      a_ph ^= 1;
+      for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
+        mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kTileN;
+        for (int kb = 0; kb < g.kb_count; ++kb) {
+          mbar_wait(&sh->full[s], ph);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kTileN;
-          for (int kb = 0; kb < g.kb_count; ++kb) {
-            mbar_wait(&sh->full[s], ph);
-            tc_fence_after();
-            const uint32_t st = smem_u32(stage_base + size_t(s) * kStage1Bytes);
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint32_t koff = ks * 256;
-              const uint64_t a_hi = make_kmajor_desc(a_base + kb * kChunkBytes + koff, g.lbo_bytes, g.sbo_bytes);
-              const uint64_t b_hi = make_kmajor_desc(st + koff, g.lbo_bytes, g.sbo_bytes);
-              mma_f16_ss(d_tmem, a_hi, b_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
-            }
+          if (elect_one()) {
+            // descriptor address field counts 16-byte units
+            const uint64_t a_d = a_desc0 + static_cast<uint64_t>(kb * (kChunkBytes >> 4));
+            const uint64_t b_d = b_desc0 + static_cast<uint64_t>(s * (kStage1Bytes >> 4));
+            mma_f16_ss(d_tmem, a_d, b_d, idesc, kb != 0 ? 1u : 0u);
+            mma_f16_ss(d_tmem, a_d + 16, b_d + 16, idesc, 1u);     // second 16-wide k step: +256 B
             tc_commit(&sh->empty[s]);
-            if (++s == n_stages) { s = 0; ph ^= 1; }
           }
-          tc_commit(&sh->tmem_full[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_ph ^= 1;
+          if (++s == n_stages) { s = 0; ph ^= 1; }
         }
-        tc_commit(&sh->a_empty);   // all MMAs that read this A panel are done
+        if (elect_one()) tc_commit(&sh->tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
       }
+      if (elect_one()) tc_commit(&sh->a_empty);   // all MMAs that read this A panel are done
     }
+    __syncwarp();
   } else {
     epilogue_role(g, epi, sh, tmem_base, warp, lane);
   }

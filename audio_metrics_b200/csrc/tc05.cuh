@@ -47,6 +47,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a fully converged warp.  Work issued under `if (elect_one())` inside a
+// loop that the WHOLE warp runs keeps loop counters and addresses warp-uniform for the
+// compiler (uniform registers, no R2UR/vote "waterfall" loops around UBLKCP / UTCMMA),
+// which a `lane == 0` branch around the loop does not.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------- bulk async copy (TMA)
 // global -> shared, completion signalled as transaction bytes on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
