@@ -41,8 +41,8 @@ struct DumpEpi {
       if (b_row0 + j < nb) C[r.a_row * ldc + b_row0 + j] = f32(acc[j]) * cv[0][c0 + j] * r.isr;
     }
   }
-  __device__ void row_end(Row& r, const ItemCoord&, int, long long, int, int) const {
-    if (checksum_only && r.a_row < na) C[r.a_row] = r.sum;
+  __device__ void row_end(Row& r, const ItemCoord&, int, long long, int, int, int) const {
+    if (checksum_only && r.a_row < na) atomicAdd(&C[r.a_row], r.sum);   // two column halves per row
   }
 };
 
@@ -50,7 +50,7 @@ struct DumpEpi {
 // Problems come in triples per subset: 3s+0 = K(f1,f1), 3s+1 = K(f2,f2),
 // 3s+2 = K(f1,f2)  (kd.py:119-122).  The diagonal of the two symmetric blocks is
 // left out here, which is kd.py:62-63's  K.sum(axis=1) - diag.  Each epilogue
-// warp writes one fp64 partial per work item: partial[item*4 + quarter].
+// warp writes one fp64 partial per work item: partial[item*8 + half*4 + quarter].
 struct KdEpi {
   static constexpr int kColVecs = 1;
   static constexpr bool kScratch = false;
@@ -115,11 +115,11 @@ struct KdEpi {
       r.sum += s;
     }
   }
-  __device__ void row_end(Row& r, const ItemCoord&, int item, long long, int quarter, int lane) const {
+  __device__ void row_end(Row& r, const ItemCoord&, int item, long long, int quarter, int lane, int half) const {
     double s = r.valid ? r.sum : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) partial[static_cast<long long>(item) * 4 + quarter] = s;
+    if (lane == 0) partial[static_cast<long long>(item) * kEpiWarps + half * 4 + quarter] = s;
   }
 };
 
@@ -153,7 +153,7 @@ __host__ __device__ inline float band_key1(float nrm_x, float rho_x, float nrm_y
 // Ranking key for row i over columns j:  t_ij = |y_j|^2 - 2 <x_i, y_j>
 // (d_ij^2 = |x_i|^2 + t_ij).  Each thread keeps its row's K smallest approximate
 // keys, with their column indices, sorted in registers across the whole column
-// sweep; one list per (split, row) leaves the kernel.  K exceeds k+1 by a margin
+// sweep; one list per (split, column half, row) leaves the kernel.  K exceeds k+1 by a margin
 // so that the refine kernel can certify that the exact (k+1)-th neighbour is
 // among the kept candidates.
 template <int K>
@@ -163,8 +163,8 @@ struct TopkEpi {
   const float* inv_a;
   const float* inv_b;
   const float* norm_b;
-  float* keys;             // [n_split][list_rows][K]
-  int* cols;               // [n_split][list_rows][K]   (-1 = empty)
+  float* keys;             // [2 * n_split][list_rows][K]   (list = 2 * split + half)
+  int* cols;               // [2 * n_split][list_rows][K]   (-1 = empty)
   long long list_rows;     // rows covered by this launch (multiple of 128)
   long long a_row_base;    // packed row of list row 0
   struct Row { float m2isr; float v[K]; int c[K]; };
@@ -193,45 +193,48 @@ struct TopkEpi {
     }
     const float tmin = fminf(fminf(m0, m1), fminf(m2, m3));
     if (__any_sync(0xffffffffu, tmin < r.v[K - 1])) {
-      // some row of the warp takes new candidates.  Each thread builds the bit mask
-      // of its qualifying columns, parks its 32 keys in its private shared-memory
-      // row, and the warp loops while any lane still has a bit to consume (usually
-      // one trip): a lane picks its lowest set column, reloads that key by dynamic
-      // index and inserts it; the threshold tightens as it goes.
-      unsigned mask = 0;
+      // some row of the warp takes new candidates.  Per 16-column half of the chunk:
+      // each thread builds the bit mask of its qualifying columns, parks the 16 keys in
+      // its private shared-memory slots, and the warp loops while any lane still has a
+      // bit to consume (usually one trip): a lane picks its lowest set column, reloads
+      // that key by dynamic index and inserts it; the threshold tightens as it goes.
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        scratch[j] = t[j];
-        mask |= (t[j] < r.v[K - 1]) ? (1u << j) : 0u;
-      }
-      while (__any_sync(0xffffffffu, mask != 0)) {
-        float key = kInf;
-        int col = -1;
-        if (mask) {
-          const int j = __ffs(mask) - 1;
-          mask &= mask - 1;
-          key = scratch[j];
-          col = static_cast<int>(b_row0) + j;
-        }
-        if (key < r.v[K - 1]) {
-          r.v[K - 1] = key;
-          r.c[K - 1] = col;
-        }
+      for (int h = 0; h < 2; ++h) {
+        unsigned mask = 0;
 #pragma unroll
-        for (int i = K - 1; i > 0; --i) {
-          const bool sw = r.v[i] < r.v[i - 1];
-          const float va = r.v[i - 1], vb = r.v[i];
-          const int ca = r.c[i - 1], cb = r.c[i];
-          r.v[i - 1] = sw ? vb : va;
-          r.v[i] = sw ? va : vb;
-          r.c[i - 1] = sw ? cb : ca;
-          r.c[i] = sw ? ca : cb;
+        for (int j = 0; j < 16; ++j) {
+          scratch[j] = t[16 * h + j];
+          mask |= (t[16 * h + j] < r.v[K - 1]) ? (1u << j) : 0u;
+        }
+        while (__any_sync(0xffffffffu, mask != 0)) {
+          float key = kInf;
+          int col = -1;
+          if (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            key = scratch[j];
+            col = static_cast<int>(b_row0) + 16 * h + j;
+          }
+          if (key < r.v[K - 1]) {
+            r.v[K - 1] = key;
+            r.c[K - 1] = col;
+          }
+#pragma unroll
+          for (int i = K - 1; i > 0; --i) {
+            const bool sw = r.v[i] < r.v[i - 1];
+            const float va = r.v[i - 1], vb = r.v[i];
+            const int ca = r.c[i - 1], cb = r.c[i];
+            r.v[i - 1] = sw ? vb : va;
+            r.v[i] = sw ? va : vb;
+            r.c[i - 1] = sw ? cb : ca;
+            r.c[i] = sw ? ca : cb;
+          }
         }
       }
     }
   }
-  __device__ void row_end(Row& r, const ItemCoord& c, int, long long a_row, int, int) const {
-    const long long o = (static_cast<long long>(c.split) * list_rows + (a_row - a_row_base)) * K;
+  __device__ void row_end(Row& r, const ItemCoord& c, int, long long a_row, int, int, int half) const {
+    const long long o = (static_cast<long long>(2 * c.split + half) * list_rows + (a_row - a_row_base)) * K;
 #pragma unroll
     for (int i = 0; i < K; ++i) { keys[o + i] = r.v[i]; cols[o + i] = r.c[i]; }
   }
@@ -247,7 +250,7 @@ struct TopkEpi {
 struct PairEntry { uint32_t i; uint32_t j_kind; };   // j_kind: bit 31 = 1 -> in_cand test
 
 struct CountEpi {
-  static constexpr int kColVecs = 3;   // 0: inv_scale_b, 1: norm_b, 2: B_hi
+  static constexpr int kColVecs = 4;   // 0: inv_scale_b, 1: norm_b, 2: B_hi, 3: B_lo
   static constexpr bool kScratch = false;
   const float* inv_a;
   const float* norm_a;
@@ -266,7 +269,9 @@ struct CountEpi {
   unsigned long long* list_count;
   unsigned long long list_cap;
   struct Row { float m2isr, nx, Alo, Ahi; bool rec, cov; uint32_t i; };
-  __device__ const float* colvec_ptr(int v) const { return v == 0 ? inv_b : (v == 1 ? norm_b : b_hi); }
+  __device__ const float* colvec_ptr(int v) const {
+    return v == 0 ? inv_b : (v == 1 ? norm_b : (v == 2 ? b_hi : b_lo));
+  }
   __device__ void row_begin(Row& r, const ItemCoord&, long long a_row) const {
     r.m2isr = -2.0f * inv_a[a_row];
     r.nx = norm_a[a_row];
@@ -291,35 +296,48 @@ struct CountEpi {
       any_ref |= (t < r.Ahi);
       any_cand |= (u < cv[2][c0 + j]);
     }
-    if (__any_sync(0xffffffffu, any_ref)) {
-      // rare: some row of this warp may have a candidate inside its ball in this chunk
-      const int lane = threadIdx.x & 31;
-      int mine = 0;
+    // Hits are rare (about k per row over the whole sweep).  A thread that has one
+    // rebuilds its comparisons as bit masks and walks the set bits on its own:
+    // certain hits are counted, hits inside the band go to the refine list.
+    if (any_ref) {
+      unsigned m_hi = 0, m_lo = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float q = f32(acc[j]) * cv[0][c0 + j];
-        const float t = fmaf(q, r.m2isr, cv[1][c0 + j]);
-        const bool sure = t < r.Alo;
-        if (!sure && t < r.Ahi) push(r.i, static_cast<uint32_t>(b_row0 + j));
-        r.cov |= sure;
-        const unsigned b = __ballot_sync(0xffffffffu, sure);
-        if (lane == j) mine = __popc(b);
+        const float t = fmaf(f32(acc[j]) * cv[0][c0 + j], r.m2isr, cv[1][c0 + j]);
+        m_hi |= (t < r.Ahi) ? (1u << j) : 0u;
+        m_lo |= (t < r.Alo) ? (1u << j) : 0u;
       }
-      if (mine) atomicAdd(col_count + b_row0 + lane, mine);
+      r.cov |= (m_lo != 0);
+      unsigned unc = m_hi & ~m_lo;
+      while (m_lo) {
+        const int j = __ffs(m_lo) - 1;
+        m_lo &= m_lo - 1;
+        atomicAdd(col_count + b_row0 + j, 1);
+      }
+      while (unc) {
+        const int j = __ffs(unc) - 1;
+        unc &= unc - 1;
+        push(r.i, static_cast<uint32_t>(b_row0 + j));
+      }
     }
     if (any_cand) {
+      unsigned m_hi = 0, m_lo = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float q = f32(acc[j]) * cv[0][c0 + j];
-        const float u = fmaf(q, r.m2isr, r.nx);
-        if (u < cv[2][c0 + j]) {
-          if (u < b_lo[b_row0 + j]) r.rec = true;
-          else push(r.i, static_cast<uint32_t>(b_row0 + j) | 0x80000000u);
-        }
+        const float u = fmaf(f32(acc[j]) * cv[0][c0 + j], r.m2isr, r.nx);
+        m_hi |= (u < cv[2][c0 + j]) ? (1u << j) : 0u;
+        m_lo |= (u < cv[3][c0 + j]) ? (1u << j) : 0u;
+      }
+      r.rec |= (m_lo != 0);
+      unsigned unc = m_hi & ~m_lo;
+      while (unc) {
+        const int j = __ffs(unc) - 1;
+        unc &= unc - 1;
+        push(r.i, static_cast<uint32_t>(b_row0 + j) | 0x80000000u);
       }
     }
   }
-  __device__ void row_end(Row& r, const ItemCoord&, int, long long a_row, int, int) const {
+  __device__ void row_end(Row& r, const ItemCoord&, int, long long a_row, int, int, int) const {
     if (a_row < a_row_end) {
       if (r.rec) row_recall[a_row - a_row_base] = 1;
       if (r.cov) row_cover[a_row - a_row_base] = 1;

@@ -75,7 +75,7 @@ static KdWs kd_ws(void* ws, int S, int m, int d) {
   w.gather = reinterpret_cast<int*>(take(static_cast<size_t>(rows) * 4));
   w.a_rb0 = reinterpret_cast<int*>(take(static_cast<size_t>(3) * S * 4));
   w.b_rb0 = reinterpret_cast<int*>(take(static_cast<size_t>(3) * S * 4));
-  w.partial = reinterpret_cast<double*>(take(static_cast<size_t>(3) * S * (w.mp / kTileM) * 4 * 8));
+  w.partial = reinterpret_cast<double*>(take(static_cast<size_t>(3) * S * (w.mp / kTileM) * kEpiWarps * 8));
   w.bytes = off;
   return w;
 }
@@ -145,7 +145,7 @@ int amb_kd_subsets(int dev, amb_stream_t stream, const void* F1, long long n1, l
   epi.m_valid = m;
   epi.partial = w.partial;
   if ((rc = launch_engine(st, dev, g, epi, "pair_engine<kd>", 3.0 * S * static_cast<double>(m) * m))) return rc;
-  kd_finalize_kernel<<<1, 256, static_cast<size_t>(S) * 8, st>>>(w.partial, S, g.n_rt * 4, m, mmd2_out, stats_out);
+  kd_finalize_kernel<<<1, 256, static_cast<size_t>(S) * 8, st>>>(w.partial, S, g.n_rt * kEpiWarps, m, mmd2_out, stats_out);
   return check_launch("kd_finalize_kernel");
 }
 

@@ -10,8 +10,11 @@
 // relative).  This is what makes the tensor-core distances usable for exact
 // neighbourhood counts and for the 1e-4 KD tolerance; a single fp16 pass is not.
 //
-// CTA = 192 threads:  warp 0 bulk-copy producer | warp 1 MMA issuer (+ TMEM
-// owner) | warps 2..5 epilogue (one TMEM lane quarter each; thread = tile row).
+// CTA = 320 threads:  warp 0 bulk-copy producer | warp 1 MMA issuer (+ TMEM
+// owner) | warps 2..9 epilogue.  A warp can only read the TMEM lane quarter
+// 32*(warp%4), so two warps share each quarter and split the tile's columns:
+// thread = (tile row, column half).  Two epilogue warps per SM sub-partition
+// hide each other's TMEM-load / shared-memory latencies.
 // Pipelines: smem ring full/empty (producer <-> MMA), TMEM double buffer
 // full/empty (MMA <-> epilogue).  Work item = (problem, row tile, column split);
 // a CTA walks items blockIdx.x, +gridDim.x, ... and, inside an item, all column
@@ -26,9 +29,11 @@ constexpr int kTileM = 128;
 constexpr int kTileN = 256;
 constexpr int kStages = 4;
 constexpr int kStageBytes = 6 * kChunkBytes;          // A hi,lo + B hi(2),lo(2) = 48 KiB
-constexpr int kEngineThreads = 192;
-constexpr int kEpiThreads = 128;
-constexpr int kMaxColVecs = 3;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kEngineThreads = 64 + kEpiThreads;
+constexpr int kMaxColVecs = 4;
+constexpr int kScratchFloats = 17;                    // 16 parked keys, odd stride: conflict-free
 constexpr uint32_t kTmemCols = 512;                    // two 256-column accumulators
 
 struct EngineGeom {
@@ -68,9 +73,9 @@ struct EngineSmem {
   uint32_t pad_;
 };
 
-// Epilogues that need it (Epi::kScratch) get 33 floats of shared memory per tile row
-// (stride 33: conflict-free), placed after EngineSmem.
-constexpr size_t kScratchBytes = size_t(kEpiThreads) * 33 * sizeof(float);
+// Epilogues that need it (Epi::kScratch) get kScratchFloats floats of shared memory per
+// epilogue thread, placed after EngineSmem.
+constexpr size_t kScratchBytes = size_t(kEpiThreads) * kScratchFloats * sizeof(float);
 template <class Epi>
 constexpr size_t engine_smem_bytes() {
   return size_t(kStages) * kStageBytes + sizeof(EngineSmem) + (Epi::kScratch ? kScratchBytes : 0);
@@ -106,20 +111,23 @@ __device__ __forceinline__ ItemCoord decode_item(const EngineGeom& g, int item) 
 //     void row_begin(Row&, const ItemCoord&, long long a_row /*packed A row*/) const;
 //     void chunk(Row&, const uint32_t (&acc)[32], const float (*cv)[kTileN], int col_in_tile,
 //                int col_in_problem, long long b_row0 /*packed B row of chunk column 0*/,
-//                float* scratch /*33 floats private to this row, or nullptr*/) const;
-//     void row_end(Row&, const ItemCoord&, int item, long long a_row, int quarter, int lane) const;
+//                float* scratch /*kScratchFloats floats private to this thread, or nullptr*/) const;
+//     void row_end(Row&, const ItemCoord&, int item, long long a_row, int quarter, int lane,
+//                  int half /*which 128 columns of every tile this thread swept*/) const;
 //   };
+// A thread sees columns [128*half, 128*half + 128) of every column tile of the item.
 
-// Epilogue role, shared by both kernels: warps 2..5, one TMEM lane quarter each.
+// Epilogue role, shared by both kernels: warps 2..9.
 template <class Epi>
 __device__ __forceinline__ void epilogue_role(const EngineGeom& g, const Epi& epi, EngineSmem* sh,
                                               uint32_t tmem_base, int warp, int lane) {
   float* scratch = Epi::kScratch
                        ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + sizeof(EngineSmem)) +
-                             (threadIdx.x - 64) * 33
+                             (threadIdx.x - 64) * kScratchFloats
                        : nullptr;
   const int n_items = g.n_problems * g.n_rt * g.n_split;
   const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
+  const int half = (warp - 2) >> 2;             // columns [128*half, +128) of each tile
   const int row_in_tile = quarter * 32 + lane;
   int acc = 0;
   uint32_t acc_ph = 0;
@@ -137,7 +145,7 @@ __device__ __forceinline__ void epilogue_role(const EngineGeom& g, const Epi& ep
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc) * kTileN +
                               (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < kTileN; c0 += 32) {
+      for (int c0 = half * (kTileN / 2); c0 < (half + 1) * (kTileN / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_addr + c0, r);
         tmem_wait_ld();
@@ -149,7 +157,7 @@ __device__ __forceinline__ void epilogue_role(const EngineGeom& g, const Epi& ep
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1;
     }
-    epi.row_end(row, c, item, a_row, quarter, lane);
+    epi.row_end(row, c, item, a_row, quarter, lane, half);
   }
 }
 
@@ -173,7 +181,7 @@ pair_engine_kernel(const EngineGeom g, const Epi epi) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sh->tmem_full[a], 1);
-      mbar_init(&sh->tmem_empty[a], 4);
+      mbar_init(&sh->tmem_empty[a], kEpiWarps);
       mbar_init(&sh->cv_full[a], 1);
     }
     fence_mbar_init();
@@ -319,7 +327,7 @@ pair_engine1_kernel(const EngineGeom g, const Epi epi) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sh->tmem_full[a], 1);
-      mbar_init(&sh->tmem_empty[a], 4);
+      mbar_init(&sh->tmem_empty[a], kEpiWarps);
       mbar_init(&sh->cv_full[a], 1);
     }
     mbar_init(&sh->a_full, 1);

@@ -348,8 +348,9 @@ static KnnWs knn_ws(void* ws, long long nrows, int Kt, int n_split) {
   size_t off = 0;
   KnnWs w;
   auto take = [&](size_t bytes) { uint8_t* p = b ? b + off : nullptr; off += static_cast<size_t>(round_up_ll(bytes, 256)); return p; };
-  w.keys = reinterpret_cast<float*>(take(static_cast<size_t>(n_split) * list_rows * Kt * 4));
-  w.cols = reinterpret_cast<int*>(take(static_cast<size_t>(n_split) * list_rows * Kt * 4));
+  // one candidate list per (column split, column half of the tile) and row
+  w.keys = reinterpret_cast<float*>(take(static_cast<size_t>(2 * n_split) * list_rows * Kt * 4));
+  w.cols = reinterpret_cast<int*>(take(static_cast<size_t>(2 * n_split) * list_rows * Kt * 4));
   w.unresolved = reinterpret_cast<int*>(take(static_cast<size_t>(nrows > 0 ? nrows : 1) * 4));
   w.n_unresolved = reinterpret_cast<int*>(take(256));
   w.max_norm = reinterpret_cast<float*>(take(256));
@@ -448,7 +449,7 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
   if (max_rows > nrows) max_rows = nrows;
   if (dtype == AMB_F32) {
     const float* Xf = static_cast<const float*>(X);
-    knn_refine_kernel<float><<<blocks, 256, 0, st>>>(Xf, ld, d, n, row0, nrows, k, Kt, n_split, list_rows, w.keys,
+    knn_refine_kernel<float><<<blocks, 256, 0, st>>>(Xf, ld, d, n, row0, nrows, k, Kt, 2 * n_split, list_rows, w.keys,
                                                      w.cols, p.norm, p.rho, sp, w.max_norm, radii, w.unresolved,
                                                      w.n_unresolved);
     if ((rc = check_launch("knn_refine_kernel"))) return rc;
@@ -456,7 +457,7 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
                                                             static_cast<int>(max_rows), radii);
   } else {
     const double* Xd = static_cast<const double*>(X);
-    knn_refine_kernel<double><<<blocks, 256, 0, st>>>(Xd, ld, d, n, row0, nrows, k, Kt, n_split, list_rows, w.keys,
+    knn_refine_kernel<double><<<blocks, 256, 0, st>>>(Xd, ld, d, n, row0, nrows, k, Kt, 2 * n_split, list_rows, w.keys,
                                                       w.cols, p.norm, p.rho, sp, w.max_norm, radii, w.unresolved,
                                                       w.n_unresolved);
     if ((rc = check_launch("knn_refine_kernel"))) return rc;
