@@ -16,6 +16,7 @@
 // The Jacobi kernel is one cooperative launch per stage: a warp owns one column
 // pair per round of a round-robin tournament, a grid barrier separates rounds.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "internal.cuh"
 
@@ -123,6 +124,253 @@ jacobi_kernel(double* __restrict__ Gt, int d, int n_mat, double tol, int* __rest
   if (blockIdx.x == 0 && threadIdx.x == 0) *sweeps_done = sweep;
 }
 
+// Block one-sided Jacobi for d <= 512: the d columns are cut into blocks of BS; a CTA
+// takes one block pair (I, J) into shared memory (2*BS rows of d doubles), one warp per
+// column pair, and runs BS rounds that rotate every column of I against every column of J
+// between two __syncthreads — a grid barrier is only needed per BLOCK round, nb-1 times
+// per sweep instead of d-1 times.  Phase 0 of a sweep rotates the pairs inside each
+// block (round robin inside I and inside J), phases 1..nb-1 the cross pairs of a
+// round-robin tournament over blocks: every column pair is visited exactly once per
+// sweep, which is a cyclic Jacobi ordering.  Same rotations, same convergence test as
+// jacobi_kernel; only the order of the pairs differs.
+template <int BS, int NR>
+__global__ void __launch_bounds__(32 * BS)
+jacobi_block_kernel(double* __restrict__ Gt, int d, int n_mat, double tol, int* __restrict__ rot_count,
+                    int* __restrict__ sweeps_done) {
+  extern __shared__ double slab[];                 // [2*BS][d]
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;               // 0 .. BS-1
+  int nb = (d + BS - 1) / BS;
+  nb += nb & 1;                                    // even number of blocks (the last may be virtual)
+  const int pairs_per_mat = nb / 2;
+  const int total = pairs_per_mat * n_mat;
+  const double tol2 = tol * tol;
+  int sweep = 0;
+  for (; sweep < kJacobiMaxSweeps; ++sweep) {
+    int my_rot = 0;
+    for (int phase = 0; phase < nb; ++phase) {
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int mat = w / pairs_per_mat, s = w - mat * pairs_per_mat;
+        int bi, bj;
+        if (phase == 0) { bi = 2 * s; bj = 2 * s + 1; }
+        else tournament_pair(nb, phase - 1, s, bi, bj);
+        double* base = Gt + static_cast<long long>(mat) * d * d;
+        // ---- load the two blocks (rows >= d are virtual: zeros, never stored)
+        for (int k = threadIdx.x; k < d; k += blockDim.x) {
+#pragma unroll 8
+          for (int r = 0; r < 2 * BS; ++r) {
+            const int row = (r < BS ? bi * BS + r : bj * BS + (r - BS));
+            slab[r * d + k] = row < d ? __ldcg(base + static_cast<long long>(row) * d + k) : 0.0;
+          }
+        }
+        __syncthreads();
+        const int inner = phase == 0 ? BS - 1 : BS;
+        for (int ir = 0; ir < inner; ++ir) {
+          int p, q;   // slab rows of this warp's pair
+          if (phase == 0) {
+            // two independent round robins, one inside each block: warps [0,BS/2) on I, the rest on J
+            const int blk = warp / (BS / 2), sl = warp % (BS / 2);
+            tournament_pair(BS, ir, sl, p, q);
+            p += blk * BS;
+            q += blk * BS;
+          } else {
+            p = warp;
+            q = BS + ((warp + ir) % BS);
+          }
+          double* gp = slab + p * d;
+          double* gq = slab + q * d;
+          double a = 0.0, b = 0.0, c = 0.0;
+          double xr[NR], yr[NR];
+#pragma unroll
+          for (int e = 0; e < NR; ++e) {
+            const int k = lane + 32 * e;
+            xr[e] = k < d ? gp[k] : 0.0;
+            yr[e] = k < d ? gq[k] : 0.0;
+            a = fma(xr[e], xr[e], a);
+            b = fma(yr[e], yr[e], b);
+            c = fma(xr[e], yr[e], c);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+          }
+          // rotate when |c| > tol sqrt(a b); with zeta = (b-a)/(2c):
+          //   t = sgn(zeta)/(|zeta| + sqrt(1+zeta^2)) = sgn(b-a) 2c / (|b-a| + sqrt((b-a)^2 + 4c^2))
+          // (one sqrt, one divide, one rsqrt instead of three of each)
+          const double ab = a * b;
+          if (ab > 0.0 && c * c > tol2 * ab) {
+            const double dl = b - a;
+            const double h = sqrt(fma(dl, dl, 4.0 * c * c));
+            double t = (2.0 * c) / (fabs(dl) + h);
+            t = dl < 0.0 ? -t : t;
+            const double cs = rsqrt(fma(t, t, 1.0));
+            const double sn = cs * t;
+#pragma unroll
+            for (int e = 0; e < NR; ++e) {
+              const int k = lane + 32 * e;
+              if (k < d) {
+                gp[k] = cs * xr[e] - sn * yr[e];
+                gq[k] = sn * xr[e] + cs * yr[e];
+              }
+            }
+            ++my_rot;
+          }
+          __syncthreads();
+        }
+        // ---- store
+        for (int k = threadIdx.x; k < d; k += blockDim.x) {
+#pragma unroll 8
+          for (int r = 0; r < 2 * BS; ++r) {
+            const int row = (r < BS ? bi * BS + r : bj * BS + (r - BS));
+            if (row < d) base[static_cast<long long>(row) * d + k] = slab[r * d + k];
+          }
+        }
+        __syncthreads();
+      }
+      grid.sync();
+    }
+    if (lane == 0 && my_rot) atomicAdd(&rot_count[sweep], my_rot);
+    grid.sync();
+    if (*reinterpret_cast<volatile int*>(&rot_count[sweep]) == 0) { ++sweep; break; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *sweeps_done = sweep;
+}
+
+// Pivoted (diagonal pivoting) Cholesky  S = L L^T  of symmetric positive SEMI-definite
+// matrices, blocked right-looking, without physical row/column swaps: step j takes the
+// not-yet-used index p with the largest residual diagonal, forms
+//   L[:, j] = (A[:, p] - Lpanel[:, :jj] Lpanel[p, :jj]^T) / sqrt(diag_p)
+// and stops at the numerical rank (diag_p <= d * eps * max diag, as LAPACK dpstrf), so a
+// rank-deficient covariance (N < d, rank-1 embedders) gives a factor with exactly `rank`
+// non-zero columns and no square roots of round-off.  L need not be triangular for what
+// follows — any factor with S = L L^T has the singular values the trace needs.
+// A: [n_mat][d][d] (overwritten by the trailing updates);  Lt: [n_mat][d][d], ZEROED by the
+// caller, row j = column j of L.  Grid = n_mat * C CTAs (cooperative): CTA 0 of each group
+// factors the PB-column panel out of shared memory, then all C CTAs of the group apply
+// A -= Lp Lp^T to their row slice.
+__global__ void __launch_bounds__(512)
+pchol_kernel(double* __restrict__ A, double* __restrict__ Lt, int d, int n_mat, int C, int PB,
+             int* __restrict__ panel_n /* [n_mat] */, int* __restrict__ rank_out /* [n_mat] */) {
+  extern __shared__ double sm[];
+  double* Lp = sm;                      // [PB][d]
+  double* dg = sm + static_cast<size_t>(PB) * d;   // [d] residual diagonal (-inf: used)
+  __shared__ double red_v[16];
+  __shared__ int red_i[16];
+  __shared__ int s_p;
+  __shared__ double s_piv;
+  cg::grid_group grid = cg::this_grid();
+  const int mat = blockIdx.x / C, c = blockIdx.x % C;
+  const bool leader = c == 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double NEG = -__longlong_as_double(0x7ff0000000000000ll);
+  double* Am = A + static_cast<long long>(mat) * d * d;
+  double* Ltm = Lt + static_cast<long long>(mat) * d * d;
+  double tol = 0.0;
+  if (leader) {
+    double mx = 0.0;
+    for (int i = tid; i < d; i += blockDim.x) {
+      const double v = Am[static_cast<long long>(i) * d + i];
+      dg[i] = v;
+      mx = fmax(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red_v[warp] = mx;
+    __syncthreads();
+    mx = 0.0;
+    for (int w = 0; w < 16; ++w) mx = fmax(mx, red_v[w]);
+    tol = static_cast<double>(d) * 2.220446049250313e-16 * mx;
+    __syncthreads();
+  }
+  const int n_panels = (d + PB - 1) / PB;
+  int j0 = 0;
+  bool finished = false;
+  for (int pan = 0; pan < n_panels; ++pan) {
+    if (leader) {
+      int npan = 0;
+      if (!finished) {
+        for (int jj = 0; jj < PB && j0 + jj < d; ++jj) {
+          // ---- pivot: arg max of the residual diagonal over unused indices
+          double bv = NEG;
+          int bi = -1;
+          for (int i = tid; i < d; i += blockDim.x) {
+            const double v = dg[i];
+            if (v > bv) { bv = v; bi = i; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi >= 0 && (bi < 0 || oi < bi))) { bv = ov; bi = oi; }
+          }
+          if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+          __syncthreads();
+          if (tid == 0) {
+            double v = red_v[0];
+            int ix = red_i[0];
+            for (int w = 1; w < 16; ++w)
+              if (red_v[w] > v || (red_v[w] == v && red_i[w] >= 0 && (ix < 0 || red_i[w] < ix))) { v = red_v[w]; ix = red_i[w]; }
+            s_p = ix;
+            s_piv = v;
+          }
+          __syncthreads();
+          const int pv = s_p;
+          const double piv = s_piv;
+          if (pv < 0 || !(piv > tol)) { finished = true; break; }   // numerical rank reached (uniform)
+          const double root = sqrt(piv);
+          const double rs = 1.0 / root;
+          for (int i = tid; i < d; i += blockDim.x) {
+            double v = __ldcg(Am + static_cast<long long>(pv) * d + i);
+            for (int k = 0; k < jj; ++k) v = fma(-Lp[k * d + i], Lp[k * d + pv], v);
+            const double di = dg[i];
+            double col = di == NEG ? 0.0 : v * rs;      // rows already used: exactly zero
+            if (i == pv) { col = root; dg[i] = NEG; }
+            else if (di != NEG) dg[i] = di - col * col;
+            Lp[jj * d + i] = col;
+          }
+          __syncthreads();
+          ++npan;
+        }
+        for (int e = tid; e < npan * d; e += blockDim.x)
+          Ltm[static_cast<long long>(j0) * d + e] = Lp[e];
+      }
+      if (tid == 0) panel_n[mat] = npan;
+    }
+    grid.sync();
+    const int npan = *reinterpret_cast<volatile int*>(panel_n + mat);
+    if (npan > 0 && pan + 1 < n_panels) {
+      if (!leader) {
+        for (int e = tid; e < npan * d; e += blockDim.x)
+          Lp[e] = __ldcg(Ltm + static_cast<long long>(j0) * d + e);
+      }
+      __syncthreads();
+      const int rows_per = (d + C - 1) / C;
+      const int r0 = c * rows_per;
+      const int r1 = min(d, r0 + rows_per);
+      for (int k = tid; k < d; k += blockDim.x) {
+        for (int i = r0; i < r1; i += 4) {
+          double acc[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int jj = 0; jj < npan; ++jj) {
+            const double l = Lp[jj * d + k];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (i + u < r1) acc[u] = fma(Lp[jj * d + i + u], l, acc[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (i + u < r1) Am[static_cast<long long>(i + u) * d + k] -= acc[u];
+        }
+      }
+    }
+    j0 += npan;
+    if (pan + 1 < n_panels) grid.sync();
+  }
+  if (leader && tid == 0) rank_out[mat] = j0;
+}
+
 // F^T row j = G^T row j / sqrt(|g_j|)   (eigenvalue lambda_j = |g_j| for PSD input)
 __global__ void factor_scale_kernel(double* __restrict__ Gt, int d, int n_mat) {
   const int lane = threadIdx.x & 31;
@@ -209,12 +457,58 @@ fad_combine_kernel(int d, const double* __restrict__ mu_x, const double* __restr
   if (threadIdx.x == 0) out[b] = red[0];
 }
 
+template <int BS, int NR>
+static int launch_jacobi_block(cudaStream_t st, int dev, double* Gt, int d, int n_mat, double tol, int* rot,
+                               int* sweeps) {
+  const size_t smem = static_cast<size_t>(2) * BS * d * sizeof(double);
+  auto* fn = jacobi_block_kernel<BS, NR>;
+  int rc = check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+                      "cudaFuncSetAttribute(jacobi_block)");
+  if (rc) return rc;
+  int per_sm = 0;
+  if ((rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * BS, smem), "occupancy"))) return rc;
+  if (per_sm < 1) return set_error(AMB_ERR_CUDA, "jacobi_block_kernel cannot be resident");
+  int nb = (d + BS - 1) / BS;
+  nb += nb & 1;
+  long long want = static_cast<long long>(nb / 2) * n_mat;
+  const long long cap = static_cast<long long>(per_sm) * sm_count(dev);
+  if (want > cap) want = cap;
+  void* args[] = {&Gt, &d, &n_mat, &tol, &rot, &sweeps};
+  rc = check_cuda(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fn), dim3(static_cast<unsigned>(want)),
+                                              dim3(32 * BS), args, smem, st),
+                  "cudaLaunchCooperativeKernel(jacobi_block_kernel)");
+  if (rc) return rc;
+  return check_launch("jacobi_block_kernel");
+}
+
 static int launch_jacobi(cudaStream_t st, int dev, double* Gt, int d, int n_mat, int* counters) {
-  const double tol = 1e-14;
+  double tol = 1e-14;
   int* rot = counters;
   int* sweeps = counters + kJacobiMaxSweeps;
   int rc = check_cuda(cudaMemsetAsync(counters, 0, (kJacobiMaxSweeps + 1) * sizeof(int), st), "memset");
   if (rc) return rc;
+  const char* env = getenv("AMB_JACOBI");   // "flat" forces the round-per-grid-barrier kernel
+  const bool flat = env && env[0] == 'f';
+  if (d <= 512 && !flat) {
+    // block size: 16 columns per block unless that leaves most SMs idle (few matrices), then 8
+    // (measured at d=512, one matrix: 15.9 / 13.1 / 15.7 ms for 16 / 8 / 4): more, smaller CTAs in
+    // flight at the price of more grid barriers per sweep
+    int bs = 16;
+    const int sms = sm_count(dev);
+    while (bs > 8 && static_cast<long long>(n_mat) * ((d + 2 * bs - 1) / (2 * bs)) * 2 <= sms) bs >>= 1;
+    if (const char* e = getenv("AMB_JACOBI_BS")) {
+      const int v = atoi(e);
+      if (v == 4 || v == 8 || v == 16) bs = v;
+    }
+#define AMB_JB(BS)                                                                                   \
+    (d <= 128 ? launch_jacobi_block<BS, 4>(st, dev, Gt, d, n_mat, tol, rot, sweeps)                    \
+     : d <= 256 ? launch_jacobi_block<BS, 8>(st, dev, Gt, d, n_mat, tol, rot, sweeps)                  \
+                : launch_jacobi_block<BS, 16>(st, dev, Gt, d, n_mat, tol, rot, sweeps))
+    if (bs == 16) return AMB_JB(16);
+    if (bs == 8) return AMB_JB(8);
+    return AMB_JB(4);
+#undef AMB_JB
+  }
   void* fn = d <= 256 ? reinterpret_cast<void*>(jacobi_kernel<8>)
              : d <= 512 ? reinterpret_cast<void*>(jacobi_kernel<16>)
                         : reinterpret_cast<void*>(jacobi_kernel<0>);
@@ -230,7 +524,7 @@ static int launch_jacobi(cudaStream_t st, int dev, double* Gt, int d, int n_mat,
   const long long cap = static_cast<long long>(per_sm) * sm_count(dev);
   if (want > cap) want = cap;
   if (want < 1) want = 1;
-  void* args[] = {&Gt, &d, &n_mat, const_cast<double*>(&tol), &rot, &sweeps};
+  void* args[] = {&Gt, &d, &n_mat, &tol, &rot, &sweeps};
   rc = check_cuda(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(want)),
                                               dim3(256), args, 0, st),
                   "cudaLaunchCooperativeKernel(jacobi_kernel)");
@@ -246,7 +540,7 @@ extern "C" {
 
 size_t amb_frechet_ws_bytes(int batch, int d) {
   if (batch <= 0 || d <= 0) return 0;
-  return static_cast<size_t>(3) * batch * d * d * 8 + 1024;
+  return static_cast<size_t>(5) * batch * d * d * 8 + 4096 + static_cast<size_t>(batch) * 16;
 }
 
 int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu_x,
@@ -255,27 +549,75 @@ int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu
   if (!mu_x || !cov_x || !mu_y || !cov_y || !out || batch <= 0 || d <= 0)
     return set_error(AMB_ERR_ARG, "amb_frechet: bad argument");
   if (d > 2048) return set_error(AMB_ERR_ARG, "amb_frechet: d=%d > 2048 not supported", d);
+  if (batch > 128) return set_error(AMB_ERR_ARG, "amb_frechet: batch=%d > 128 (split the call)", batch);
   const size_t need = amb_frechet_ws_bytes(batch, d);
   if (!ws || ws_bytes < need) return set_error(AMB_ERR_WS, "amb_frechet: workspace %zu < %zu", ws_bytes, need);
   DeviceGuard guard(dev);
   if (!guard.ok) return AMB_ERR_CUDA;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t mat = static_cast<size_t>(d) * d;
-  double* G = static_cast<double*>(ws);          // [2*batch] : x factors then y factors
-  double* Mt = G + 2 * batch * mat;              // [batch]
-  int* counters = reinterpret_cast<int*>(Mt + batch * mat);
+  double* G = static_cast<double*>(ws);          // [2*batch] : covariance copies, x then y
+  double* Lt = G + 2 * batch * mat;              // [2*batch] : factors (row j = column j), x then y
+  double* Mt = Lt + 2 * batch * mat;             // [batch]
+  int* counters = reinterpret_cast<int*>(Mt + batch * mat);     // 1024 ints
+  int* panel_n = counters + 512;                                // [2*batch] + rank [2*batch]
   int rc;
+  if ((rc = check_cuda(cudaMemsetAsync(counters, 0, 4096, st), "memset"))) return rc;
   if ((rc = check_cuda(cudaMemcpyAsync(G, cov_x, batch * mat * 8, cudaMemcpyDeviceToDevice, st), "memcpy"))) return rc;
   if ((rc = check_cuda(cudaMemcpyAsync(G + batch * mat, cov_y, batch * mat * 8, cudaMemcpyDeviceToDevice, st), "memcpy"))) return rc;
-  if ((rc = launch_jacobi(st, dev, G, d, 2 * batch, counters))) return rc;
-  factor_scale_kernel<<<(2 * batch * d * 32 + 255) / 256, 256, 0, st>>>(G, d, 2 * batch);
-  if ((rc = check_launch("factor_scale_kernel"))) return rc;
+  const char* mode = getenv("AMB_FAD_FACTOR");   // "eig": eigen-factors by Jacobi (the slower first implementation)
+  double* F = Lt;
+  if (mode && mode[0] == 'e') {
+    if ((rc = launch_jacobi(st, dev, G, d, 2 * batch, counters))) return rc;
+    factor_scale_kernel<<<(2 * batch * d * 32 + 255) / 256, 256, 0, st>>>(G, d, 2 * batch);
+    if ((rc = check_launch("factor_scale_kernel"))) return rc;
+    F = G;
+  } else {
+    if ((rc = check_cuda(cudaMemsetAsync(Lt, 0, 2 * batch * mat * 8, st), "memset"))) return rc;
+    const int PB = d <= 512 ? 32 : (d <= 1024 ? 16 : 8);
+    const size_t smem = (static_cast<size_t>(PB) * d + d) * sizeof(double);
+    if ((rc = check_cuda(cudaFuncSetAttribute(pchol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(smem)), "cudaFuncSetAttribute(pchol)"))) return rc;
+    const int sms = sm_count(dev);
+    // matrices per cooperative launch: all CTAs must be co-resident (one per SM at this smem size)
+    for (int m0 = 0; m0 < 2 * batch; m0 += sms) {
+      int n_mat = 2 * batch - m0 < sms ? 2 * batch - m0 : sms;
+      int C = sms / n_mat;
+      if (C > 16) C = 16;
+      double* Ap = G + static_cast<size_t>(m0) * mat;
+      double* Lp = Lt + static_cast<size_t>(m0) * mat;
+      int* pn = panel_n + m0;
+      int* rk = panel_n + 2 * batch + m0;
+      int dd = d, pb = PB;
+      void* args[] = {&Ap, &Lp, &dd, &n_mat, &C, &pb, &pn, &rk};
+      rc = check_cuda(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(pchol_kernel), dim3(n_mat * C), dim3(512),
+                                                  args, smem, st), "cudaLaunchCooperativeKernel(pchol_kernel)");
+      if (rc) return rc;
+      if ((rc = check_launch("pchol_kernel"))) return rc;
+    }
+  }
   dim3 ggrid((d + 63) / 64, (d + 63) / 64, batch);
-  dgemm_nt_kernel<<<ggrid, 256, 0, st>>>(G, G + batch * mat, Mt, d);   // Mt = Fx^T-rows . Fy^T-rows
+  dgemm_nt_kernel<<<ggrid, 256, 0, st>>>(F, F + batch * mat, Mt, d);   // Mt[i][j] = <F_x col i, F_y col j>
   if ((rc = check_launch("dgemm_nt_kernel"))) return rc;
   if ((rc = launch_jacobi(st, dev, Mt, d, batch, counters + 64))) return rc;
   fad_combine_kernel<<<batch, 256, 0, st>>>(d, mu_x, cov_x, mu_y, cov_y, Mt, out);
-  return check_launch("fad_combine_kernel");
+  if ((rc = check_launch("fad_combine_kernel"))) return rc;
+  if (getenv("AMB_FAD_DEBUG")) {   // ranks, sweeps / rotations per sweep of the Jacobi stages (synchronises)
+    int h[1024] = {0};
+    if (cudaStreamSynchronize(st) == cudaSuccess &&
+        cudaMemcpy(h, counters, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "[amb] factor ranks:");
+      for (int i = 0; i < 2 * batch && i < 16; ++i) fprintf(stderr, " %d", h[512 + 2 * batch + i]);
+      fprintf(stderr, "\n");
+      for (int stage = 0; stage < 2; ++stage) {
+        const int* c = h + stage * 64;
+        fprintf(stderr, "[amb] jacobi stage %d: %d sweeps, rotations:", stage ? 3 : 1, c[kJacobiMaxSweeps]);
+        for (int i = 0; i < c[kJacobiMaxSweeps] && i < kJacobiMaxSweeps; ++i) fprintf(stderr, " %d", c[i]);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
+  return AMB_OK;
 }
 
 }  // extern "C"
