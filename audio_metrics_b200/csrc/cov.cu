@@ -3,6 +3,8 @@
 // (products of fp32 inputs are exact in fp64, so the only rounding is the fp64
 // summation), then finalised to (mean, unbiased covariance) and merged with
 // Chan's pairwise update.
+#include <cstdlib>
+
 #include "internal.cuh"
 
 namespace amb {
@@ -160,6 +162,16 @@ static int cov_slabs(long long n, int d) {
   return static_cast<int>(s);
 }
 
+// fp32 inputs with enough rows go through the exact integer tensor-core path (cov_tc.cu);
+// small batches (the 32-row streaming adds) and fp64 inputs stay on the FP64 pipe.
+// AMB_COV=dfma forces the FP64-pipe kernel.
+constexpr long long kCovTcMinRows = 4096;
+static bool use_cov_tc(int dtype, long long n) {
+  if (dtype != AMB_F32 || n < kCovTcMinRows) return false;
+  const char* e = getenv("AMB_COV");
+  return !(e && e[0] == 'd');
+}
+
 }  // namespace amb
 
 using namespace amb;
@@ -169,7 +181,9 @@ extern "C" {
 size_t amb_cov_ws_bytes(long long n, int d) {
   if (n <= 0 || d <= 0) return 0;
   const int s = cov_slabs(n, d);
-  return static_cast<size_t>(s) * (static_cast<size_t>(d) * d + d) * 8 + 256;
+  const size_t dfma = static_cast<size_t>(s) * (static_cast<size_t>(d) * d + d) * 8 + 256;
+  const size_t tc = n >= kCovTcMinRows ? cov_tc_ws_bytes(n, d) : 0;
+  return dfma > tc ? dfma : tc;
 }
 
 int amb_cov_accumulate(int dev, amb_stream_t stream, const void* X, int dtype, long long n, int d,
@@ -182,6 +196,7 @@ int amb_cov_accumulate(int dev, amb_stream_t stream, const void* X, int dtype, l
   DeviceGuard guard(dev);
   if (!guard.ok) return AMB_ERR_CUDA;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_cov_tc(dtype, n)) return cov_tc_accumulate(st, dev, static_cast<const float*>(X), n, d, ld, sum, gram, ws);
   const int slabs = cov_slabs(n, d);
   const int nt = (d + kGT - 1) / kGT;
   double* gpart = static_cast<double*>(ws);

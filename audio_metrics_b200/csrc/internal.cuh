@@ -58,4 +58,9 @@ int launch_pack(cudaStream_t stream, const void* src, int dtype, long long ld, i
                 long long n_rows_out, __half* planes, long long plane_halfs, int kb_count,
                 float* inv_scale, float* norm, float* rho);
 
+// Integer tensor-core Gram / column sums of an fp32 matrix (cov_tc.cu).
+size_t cov_tc_ws_bytes(long long n, int d);
+int cov_tc_accumulate(cudaStream_t st, int dev, const float* X, long long n, int d, long long ld, double* sum,
+                      double* gram, void* ws);
+
 }  // namespace amb
