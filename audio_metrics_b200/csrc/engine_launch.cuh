@@ -57,7 +57,11 @@ int launch_engine1(cudaStream_t stream, int dev, EngineGeom g, const Epi& epi, c
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(pair_engine1)");
   const long long items = static_cast<long long>(g.n_problems) * g.n_rt * g.n_split;
   if (items <= 0) return AMB_OK;
-  const int sms = sm_count(dev);
+  int sms = sm_count(dev);
+  if (const char* e = getenv("AMB_GRID")) {   // experiment knob: fewer persistent CTAs than SMs
+    const int v = atoi(e);
+    if (v >= 1 && v < sms) sms = v;
+  }
   const unsigned grid = static_cast<unsigned>(items < sms ? items : sms);
   const double exec_flops = static_cast<double>(g.n_problems) * g.n_rt * g.n_ct * (2.0 * kTileM * kTileN) *
                             (g.kb_count * static_cast<double>(kBlockK));

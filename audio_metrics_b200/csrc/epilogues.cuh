@@ -23,7 +23,7 @@ struct DumpEpi {
   int checksum_only;       // 1: C[a_row] = sum_j dot (timing runs; no N x M write)
   struct Row { float isr; long long a_row; float sum; };
   __device__ const float* colvec_ptr(int) const { return inv_b; }
-  __device__ void row_begin(Row& r, const ItemCoord&, long long a_row) const {
+  __device__ void row_begin(Row& r, const ItemCoord&, long long a_row, int, float*) const {
     r.isr = inv_a[a_row];
     r.a_row = a_row;
     r.sum = 0.f;
@@ -66,7 +66,7 @@ struct KdEpi {
   double* partial;
   struct Row { double sum; double gr; float na; int row_in_problem; bool valid; bool sym; };
   __device__ const float* colvec_ptr(int) const { return inv_b; }
-  __device__ void row_begin(Row& r, const ItemCoord& c, long long a_row) const {
+  __device__ void row_begin(Row& r, const ItemCoord& c, long long a_row, int, float*) const {
     r.row_in_problem = c.rt * kTileM + static_cast<int>(a_row % kTileM);
     r.valid = r.row_in_problem < m_valid;
     r.sym = (c.problem % 3) != 2;
@@ -167,12 +167,21 @@ struct TopkEpi {
   int* cols;               // [2 * n_split][list_rows][K]   (-1 = empty)
   long long list_rows;     // rows covered by this launch (multiple of 128)
   long long a_row_base;    // packed row of list row 0
-  struct Row { float m2isr; float v[K]; int c[K]; };
+  // mine / peer: where the two threads of a row (one per column half) publish their current
+  // K-th smallest key.  A key that is not below the OTHER half's K-th smallest cannot be among
+  // the row's K smallest overall, so each half filters with the minimum of the two — the two
+  // lists together then take about as many insertions as one list over all columns would.
+  // The refine kernel's certificate is unaffected: whatever a list rejected was >= some list's
+  // K-th key at that time >= that list's final K-th key >= the K-th smallest of the union.
+  struct Row { float m2isr; float v[K]; int c[K]; float* mine; const volatile float* peer; };
   __device__ const float* colvec_ptr(int v) const { return v == 0 ? inv_b : norm_b; }
-  __device__ void row_begin(Row& r, const ItemCoord&, long long a_row) const {
+  __device__ void row_begin(Row& r, const ItemCoord&, long long a_row, int half, float* xchg) const {
     r.m2isr = -2.0f * inv_a[a_row];
 #pragma unroll
     for (int i = 0; i < K; ++i) { r.v[i] = kInf; r.c[i] = -1; }
+    r.mine = xchg + half;
+    r.peer = xchg + (half ^ 1);
+    *r.mine = kInf;
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
                         long long b_row0, float* scratch) const {
@@ -192,7 +201,8 @@ struct TopkEpi {
       m3 = fminf(m3, t[j + 3]);
     }
     const float tmin = fminf(fminf(m0, m1), fminf(m2, m3));
-    if (__any_sync(0xffffffffu, tmin < r.v[K - 1])) {
+    const float thr = fminf(r.v[K - 1], *r.peer);
+    if (__any_sync(0xffffffffu, tmin < thr)) {
       // some row of the warp takes new candidates.  Per 16-column half of the chunk:
       // each thread builds the bit mask of its qualifying columns, parks the 16 keys in
       // its private shared-memory slots, and the warp loops while any lane still has a
@@ -204,7 +214,7 @@ struct TopkEpi {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           scratch[j] = t[16 * h + j];
-          mask |= (t[16 * h + j] < r.v[K - 1]) ? (1u << j) : 0u;
+          mask |= (t[16 * h + j] < thr) ? (1u << j) : 0u;
         }
         while (__any_sync(0xffffffffu, mask != 0)) {
           float key = kInf;
@@ -231,6 +241,7 @@ struct TopkEpi {
           }
         }
       }
+      *r.mine = r.v[K - 1];
     }
   }
   __device__ void row_end(Row& r, const ItemCoord& c, int, long long a_row, int, int, int half) const {
@@ -272,7 +283,7 @@ struct CountEpi {
   __device__ const float* colvec_ptr(int v) const {
     return v == 0 ? inv_b : (v == 1 ? norm_b : (v == 2 ? b_hi : b_lo));
   }
-  __device__ void row_begin(Row& r, const ItemCoord&, long long a_row) const {
+  __device__ void row_begin(Row& r, const ItemCoord&, long long a_row, int, float*) const {
     r.m2isr = -2.0f * inv_a[a_row];
     r.nx = norm_a[a_row];
     r.Alo = a_lo[a_row];

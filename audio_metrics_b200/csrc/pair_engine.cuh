@@ -74,8 +74,9 @@ struct EngineSmem {
 };
 
 // Epilogues that need it (Epi::kScratch) get kScratchFloats floats of shared memory per
-// epilogue thread, placed after EngineSmem.
-constexpr size_t kScratchBytes = size_t(kEpiThreads) * kScratchFloats * sizeof(float);
+// epilogue thread, placed after EngineSmem, followed by two floats per tile row through
+// which the two threads of a row (column halves) can exchange a value.
+constexpr size_t kScratchBytes = size_t(kEpiThreads) * kScratchFloats * sizeof(float) + size_t(kTileM) * 2 * sizeof(float);
 template <class Epi>
 constexpr size_t engine_smem_bytes() {
   return size_t(kStages) * kStageBytes + sizeof(EngineSmem) + (Epi::kScratch ? kScratchBytes : 0);
@@ -108,7 +109,9 @@ __device__ __forceinline__ ItemCoord decode_item(const EngineGeom& g, int item) 
 //     static constexpr bool kScratch;                // wants the per-row scratch area
 //     struct Row;                                    // per-thread (= per tile row) state
 //     const float* colvec_ptr(int v) const;          // global array, indexed by packed B row
-//     void row_begin(Row&, const ItemCoord&, long long a_row /*packed A row*/) const;
+//     void row_begin(Row&, const ItemCoord&, long long a_row /*packed A row*/, int half,
+//                    float* xchg /*2 floats shared by the two threads of this tile row, or nullptr;
+//                                  both threads pass a 64-thread barrier after row_begin*/) const;
 //     void chunk(Row&, const uint32_t (&acc)[32], const float (*cv)[kTileN], int col_in_tile,
 //                int col_in_problem, long long b_row0 /*packed B row of chunk column 0*/,
 //                float* scratch /*kScratchFloats floats private to this thread, or nullptr*/) const;
@@ -129,6 +132,9 @@ __device__ __forceinline__ void epilogue_role(const EngineGeom& g, const Epi& ep
   const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
   const int half = (warp - 2) >> 2;             // columns [128*half, +128) of each tile
   const int row_in_tile = quarter * 32 + lane;
+  float* xchg = Epi::kScratch ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + sizeof(EngineSmem)) +
+                                    kEpiThreads * kScratchFloats + row_in_tile * 2
+                              : nullptr;
   int acc = 0;
   uint32_t acc_ph = 0;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -136,7 +142,8 @@ __device__ __forceinline__ void epilogue_role(const EngineGeom& g, const Epi& ep
     const long long a_row = ((g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + c.rt) * static_cast<long long>(kTileM) + row_in_tile;
     const long long b_row_base = static_cast<long long>((g.b_rb0 ? g.b_rb0[c.problem] : 0) + g.b_rb_base) * kBlockRows;
     typename Epi::Row row;
-    epi.row_begin(row, c, a_row);
+    epi.row_begin(row, c, a_row, half, xchg);
+    if (Epi::kScratch) named_bar_sync(1 + quarter, 64);   // both column halves of the quarter are in this item
     for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
       const long long b_row0 = b_row_base + static_cast<long long>(ct) * kTileN;
       mbar_wait(&sh->cv_full[acc], acc_ph);     // column vectors landed (producer bulk copy)

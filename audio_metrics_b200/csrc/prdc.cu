@@ -280,15 +280,17 @@ __global__ void prdc_reduce_kernel(const int32_t* __restrict__ col_count, long l
 }
 
 // ------------------------------------------------------------------ host side
-// Candidates kept per row.  The margin beyond k+1 is what lets the refine kernel
-// certify its answer: the (k+1)-th exact distance must sit below the Kt-th
-// approximate key by more than the error band.
+// Candidates kept per row: twice the k+1 that are needed.  The margin is what lets the
+// refine kernel certify its answer: the (k+1)-th exact distance must sit below the Kt-th
+// approximate key by more than the error band (rows that fail go to the brute-force
+// kernel).  The sorted-insert cost of the epilogue grows like Kt^2, so Kt is not padded
+// to a power of two.
 static int pick_kt(int k) {
   if (k + 1 > 30) return 0;
-  const int need = 2 * (k + 1) + 4;
-  if (need <= 8) return 8;
-  if (need <= 16) return 16;
-  return 32;
+  const int need = 2 * (k + 1);
+  for (int kt : {8, 12, 16, 24, 32})
+    if (need <= kt) return kt;
+  return 32;   // 16 <= k <= 29: at least k + 3 candidates
 }
 
 // Column splits per row tile.  Items are numbered split-major and dealt round-robin
@@ -437,9 +439,12 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
   g.n_split = n_split;
   g.lbo_bytes = 128;
   g.sbo_bytes = 512;
-  if (Kt == 8) rc = run_topk<8>(st, dev, g, p, w, list_rows, row0, static_cast<double>(nrows) * n, sp);
-  else if (Kt == 16) rc = run_topk<16>(st, dev, g, p, w, list_rows, row0, static_cast<double>(nrows) * n, sp);
-  else rc = run_topk<32>(st, dev, g, p, w, list_rows, row0, static_cast<double>(nrows) * n, sp);
+  const double alg_pairs = static_cast<double>(nrows) * n;
+  if (Kt == 8) rc = run_topk<8>(st, dev, g, p, w, list_rows, row0, alg_pairs, sp);
+  else if (Kt == 12) rc = run_topk<12>(st, dev, g, p, w, list_rows, row0, alg_pairs, sp);
+  else if (Kt == 16) rc = run_topk<16>(st, dev, g, p, w, list_rows, row0, alg_pairs, sp);
+  else if (Kt == 24) rc = run_topk<24>(st, dev, g, p, w, list_rows, row0, alg_pairs, sp);
+  else rc = run_topk<32>(st, dev, g, p, w, list_rows, row0, alg_pairs, sp);
   if (rc) return rc;
 
   const unsigned blocks = static_cast<unsigned>((nrows * 32 + 255) / 256);

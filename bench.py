@@ -289,7 +289,7 @@ def run_b200_arm(args):
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops"], "traffic": load_traffic(),
-        "kernel": "pair_engine_kernel<TopkEpi|CountEpi|KdEpi> (tcgen05, fp16 hi/lo split: 3 MMAs per product)",
+        "kernel": "pair_engine1_kernel<TopkEpi|CountEpi> (tcgen05 kind::f16, one MMA per product, A panel resident in smem) + pair_engine_kernel<KdEpi> (3-MMA split)",
         "launches_timed": int(eng_launches), "avg_launch_ms": eng_ms / eng_launches if eng_launches else None,
         "kernel_share_of_step": eng_ms / (ms_step * args.steps) if ms_step > 0 else None,
         "executed_tflops": executed, "executed_frac": executed / peaks["tflops"], "peak_source": peaks["source"],
@@ -311,7 +311,7 @@ def run_b200_arm(args):
     line = {
         "metric": METRIC, "value": pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f16x2-split MMA -> f32 accumulate, f64 refine/statistics", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f16 MMA filter (f32 accumulate) + f64 exact refine; KD f16x2 split; statistics i8 digit MMA (exact) / f64", "data": "synthetic",
         "config": config_dict(world),
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
