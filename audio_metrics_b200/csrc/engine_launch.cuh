@@ -43,7 +43,7 @@ template <class Epi>
 int launch_engine1(cudaStream_t stream, int dev, EngineGeom g, const Epi& epi, const char* what,
                    double alg_pairs = 0.0) {
   if (g.kb_count > kMaxResidentKb) return set_error(AMB_ERR_ARG, "%s: kb_count %d too large for the resident panel", what, g.kb_count);
-  const size_t fixed = size_t(g.kb_count) * kChunkBytes + sizeof(EngineSmem) + (Epi::kScratch ? kScratchBytes : 0);
+  const size_t fixed = size_t(g.kb_count) * kChunkBytes + sizeof(EngineSmemOf<Epi>) + (Epi::kScratch ? kScratchBytes : 0);
   int n_stages = static_cast<int>((kMaxDynSmem - fixed) / kStage1Bytes);
   if (n_stages > kMaxStages) n_stages = kMaxStages;
   if (const char* e = getenv("AMB_STAGES")) {   // tuning knob: shallower B ring

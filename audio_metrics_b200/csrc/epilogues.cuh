@@ -203,18 +203,18 @@ struct TopkEpi {
     const float tmin = fminf(fminf(m0, m1), fminf(m2, m3));
     const float thr = fminf(r.v[K - 1], *r.peer);
     if (__any_sync(0xffffffffu, tmin < thr)) {
-      // some row of the warp takes new candidates.  Per 16-column half of the chunk:
-      // each thread builds the bit mask of its qualifying columns, parks the 16 keys in
+      // some row of the warp takes new candidates.  Per 8-column group of the chunk:
+      // each thread builds the bit mask of its qualifying columns, parks the 8 keys in
       // its private shared-memory slots, and the warp loops while any lane still has a
       // bit to consume (usually one trip): a lane picks its lowest set column, reloads
       // that key by dynamic index and inserts it; the threshold tightens as it goes.
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < 4; ++h) {
         unsigned mask = 0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          scratch[j] = t[16 * h + j];
-          mask |= (t[16 * h + j] < thr) ? (1u << j) : 0u;
+        for (int j = 0; j < 8; ++j) {
+          scratch[j] = t[8 * h + j];
+          mask |= (t[8 * h + j] < thr) ? (1u << j) : 0u;
         }
         while (__any_sync(0xffffffffu, mask != 0)) {
           float key = kInf;
@@ -223,7 +223,7 @@ struct TopkEpi {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
             key = scratch[j];
-            col = static_cast<int>(b_row0) + 16 * h + j;
+            col = static_cast<int>(b_row0) + 8 * h + j;
           }
           if (key < r.v[K - 1]) {
             r.v[K - 1] = key;

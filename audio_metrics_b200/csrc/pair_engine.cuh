@@ -32,8 +32,7 @@ constexpr int kStageBytes = 6 * kChunkBytes;          // A hi,lo + B hi(2),lo(2)
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kEngineThreads = 64 + kEpiThreads;
-constexpr int kMaxColVecs = 4;
-constexpr int kScratchFloats = 17;                    // 16 parked keys, odd stride: conflict-free
+constexpr int kScratchFloats = 9;                     // 8 parked keys, odd stride: conflict-free
 constexpr uint32_t kTmemCols = 512;                    // two 256-column accumulators
 
 struct EngineGeom {
@@ -60,8 +59,9 @@ struct EngineGeom {
 };
 
 constexpr int kMaxStages = 8;
-struct EngineSmem {
-  alignas(128) float colvec[2][kMaxColVecs][kTileN];   // bulk-copy destinations: keep 16 B aligned
+template <int NCV>
+struct EngineSmemT {
+  alignas(128) float colvec[2][NCV][kTileN];   // bulk-copy destinations: keep 16 B aligned
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
@@ -78,8 +78,10 @@ struct EngineSmem {
 // which the two threads of a row (column halves) can exchange a value.
 constexpr size_t kScratchBytes = size_t(kEpiThreads) * kScratchFloats * sizeof(float) + size_t(kTileM) * 2 * sizeof(float);
 template <class Epi>
+using EngineSmemOf = EngineSmemT<Epi::kColVecs>;
+template <class Epi>
 constexpr size_t engine_smem_bytes() {
-  return size_t(kStages) * kStageBytes + sizeof(EngineSmem) + (Epi::kScratch ? kScratchBytes : 0);
+  return size_t(kStages) * kStageBytes + sizeof(EngineSmemOf<Epi>) + (Epi::kScratch ? kScratchBytes : 0);
 }
 
 struct ItemCoord {
@@ -122,8 +124,9 @@ __device__ __forceinline__ ItemCoord decode_item(const EngineGeom& g, int item) 
 
 // Epilogue role, shared by both kernels: warps 2..9.
 template <class Epi>
-__device__ __forceinline__ void epilogue_role(const EngineGeom& g, const Epi& epi, EngineSmem* sh,
+__device__ __forceinline__ void epilogue_role(const EngineGeom& g, const Epi& epi, EngineSmemOf<Epi>* sh,
                                               uint32_t tmem_base, int warp, int lane) {
+  using EngineSmem = EngineSmemOf<Epi>;
   float* scratch = Epi::kScratch
                        ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + sizeof(EngineSmem)) +
                              (threadIdx.x - 64) * kScratchFloats
@@ -173,6 +176,7 @@ __global__ void __launch_bounds__(kEngineThreads, 1)
 pair_engine_kernel(const EngineGeom g, const Epi epi) {
   // no pointer laundering here: everything derived from smem_buf stays in the
   // shared address space for the compiler (LDS/STS instead of generic LD/ST)
+  using EngineSmem = EngineSmemOf<Epi>;
   extern __shared__ __align__(1024) uint8_t smem_buf[];
   uint8_t* stage_base = smem_buf;
   EngineSmem* sh = reinterpret_cast<EngineSmem*>(smem_buf + size_t(kStages) * kStageBytes);
@@ -317,6 +321,7 @@ constexpr int kMaxResidentKb = 16;
 template <class Epi>
 __global__ void __launch_bounds__(kEngineThreads, 1)
 pair_engine1_kernel(const EngineGeom g, const Epi epi) {
+  using EngineSmem = EngineSmemOf<Epi>;
   extern __shared__ __align__(1024) uint8_t smem_buf[];
   uint8_t* a_panel = smem_buf;                                           // kb_count chunks
   uint8_t* stage_base = smem_buf + size_t(g.kb_count) * kChunkBytes;
