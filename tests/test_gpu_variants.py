@@ -1,0 +1,171 @@
+"""GPU tests of the alternative code paths behind the same entry points, and of
+size-independent properties at BASELINE.json's full size (200k x 512).
+
+* the single-MMA filter (d <= 512) and the three-MMA split sweep must give the SAME
+  radii and counts, because both are only filters in front of the exact fp64 refine;
+* the integer tensor-core covariance (fp32, n >= 4096) against the fp64 oracle on
+  inputs chosen to stress its per-column fixed-point grid;
+* the pivoted-Cholesky factor path of the Frechet distance against the Jacobi
+  eigen-factor path and the oracle on rank-deficient statistics.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle.prdc import cdist_exact
+from audio_metrics_b200 import AudioMetricsData, frechet_distance, prdc
+from audio_metrics_b200.metrics.prdc import nearest_neighbour_distances, prdc_totals
+from audio_metrics_b200.synth import make_sets_numpy, make_sets_torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _amd(x, store=True):
+    a = AudioMetricsData(store_embeddings=store)
+    a.add(torch.from_numpy(x) if isinstance(x, np.ndarray) else x)
+    return a
+
+
+def _stats64(x):
+    m, c, _ = oracle.batch_stats(x, compute_dtype=np.dtype(np.float64))
+    return m, c
+
+
+# ------------------------------------------------------------------ engine variants
+@pytest.mark.parametrize("n,m,d,k", [(3000, 2600, 512, 5), (1500, 1500, 96, 10), (2000, 1000, 300, 2)])
+def test_single_pass_and_split_sweeps_agree(cuda_device, monkeypatch, n, m, d, k):
+    ref, cand = make_sets_numpy(n, m, d, seed=n + d + k)
+    out = {}
+    for passes in ("1", "3"):
+        monkeypatch.setenv("AMB_PASSES", passes)
+        R, C = _amd(ref), _amd(cand)
+        r_ref = nearest_neighbour_distances(R, k)
+        col, rec, cov, tot = prdc_totals(R, C, k)
+        out[passes] = (r_ref.cpu().numpy(), col.cpu().numpy(), rec.cpu().numpy(), cov.cpu().numpy(), int(tot[4]))
+    for a, b in zip(out["1"][:4], out["3"][:4]):
+        assert np.array_equal(a, b)
+    # the single-pass band is wider: more pairs go through the exact refine
+    assert out["1"][4] >= out["3"][4]
+
+
+def test_wide_embeddings_use_the_split_sweep(cuda_device):
+    """d > 512 does not fit the resident A panel: the three-MMA kernel runs, same contract."""
+    ref, cand = make_sets_numpy(700, 600, 700, seed=9)
+    got = nearest_neighbour_distances(torch.from_numpy(ref), 5).cpu().numpy()
+    exact = np.partition(cdist_exact(ref, ref), 5, axis=-1)[:, 5]
+    np.testing.assert_allclose(got, exact.astype(np.float32), rtol=2e-7, atol=1e-12)
+    out = prdc(_amd(ref), _amd(cand), 5)
+    want = oracle.prdc(ref, cand, 5)
+    for key in want:
+        assert abs(out[key] - want[key]) <= 3 / 600, (key, out[key], want[key])
+
+
+def test_row_shards_reassemble(cuda_device):
+    """Radii and counts of 128-aligned row shards equal the unsharded result bit for bit
+    (what dist.evaluate_sharded relies on)."""
+    ref, cand = make_sets_numpy(5000, 4100, 256, seed=21)
+    R, C = _amd(ref), _amd(cand)
+    k = 5
+    full = nearest_neighbour_distances(R, k)
+    parts = torch.cat([nearest_neighbour_distances(R, k, row_range=(r0, min(5000, r0 + 1792) - r0))
+                       for r0 in range(0, 5000, 1792)])
+    assert torch.equal(full, parts)
+    r_ref, r_cand = R.get_radii(k), C.get_radii(k)
+    col, rec, cov, _ = prdc_totals(R, C, k)
+    col2 = torch.zeros_like(col)
+    rec2, cov2 = [], []
+    for r0 in range(0, 5000, 1792):
+        c_, r_, v_, _ = prdc_totals(R, C, k, row_range=(r0, min(5000, r0 + 1792) - r0), ref_radii=r_ref, cand_radii=r_cand)
+        col2 += c_
+        rec2.append(r_); cov2.append(v_)
+    assert torch.equal(col, col2) and torch.equal(rec, torch.cat(rec2)) and torch.equal(cov, torch.cat(cov2))
+
+
+# ------------------------------------------------------------ tensor-core covariance
+def test_tensor_core_covariance_stress(cuda_device):
+    rng = np.random.default_rng(5)
+    n, d = 9000, 70
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x[:, 0] = 0.0                                    # all-zero column
+    x[:, 1] = 3.25                                   # constant column: zero variance, large mean
+    x[:, 2] = x[:, 3]                                # duplicate columns: singular covariance
+    x[:, 4] *= 1e-6                                  # tiny scale
+    x[:, 5] *= 1e6                                   # huge scale
+    x[::1000, 6] = 5e3                               # heavy tail: max >> rms
+    x[:, 7] = 100.0 + 1e-3 * x[:, 7]                 # mean >> spread: cancellation in G - n mu mu^T
+    a = _amd(x, store=False)
+    m_ref, c_ref = _stats64(x)
+    mean, cov = a.mean.cpu().numpy(), a.cov.cpu().numpy()
+    colmax = np.abs(x).max(axis=0).astype(np.float64)
+    grid = 2.0 ** -30 * np.maximum(colmax, 1e-300) * 2     # one step of the column's fixed-point grid
+    assert (np.abs(mean - m_ref) <= 0.5 * grid + 1e-15 * np.abs(m_ref)).all()
+    # covariance error: first order in the rounding of each column, |x_k| * grid_l / sqrt(n) scale
+    sd = np.sqrt(np.maximum(np.diag(c_ref), 0.0)) + np.abs(m_ref)
+    bound = np.outer(sd + grid, grid) + np.outer(grid, sd + grid)
+    assert (np.abs(cov - c_ref) <= bound + 1e-12 * np.abs(c_ref)).all()
+    assert cov[0, 0] == 0.0 and abs(cov[1, 1]) <= 1e-12
+    np.testing.assert_allclose(cov[2, 3], cov[2, 2], rtol=1e-12)
+    # well-scaled columns are as good as the FP64-pipe path
+    np.testing.assert_allclose(cov[8:, 8:], c_ref[8:, 8:], rtol=1e-8, atol=1e-10)
+
+
+def test_covariance_paths_agree_and_stream(cuda_device, monkeypatch):
+    ref, _ = make_sets_numpy(10000, 8, 512, seed=2)
+    tc = _amd(ref, store=False)
+    monkeypatch.setenv("AMB_COV", "dfma")
+    fp = _amd(ref, store=False)
+    monkeypatch.delenv("AMB_COV")
+    np.testing.assert_allclose(tc.cov.cpu().numpy(), fp.cov.cpu().numpy(), rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(tc.mean.cpu().numpy(), fp.mean.cpu().numpy(), rtol=0, atol=2.0 ** -30)
+    # two tensor-core blocks merged by Chan's update == one block (reference tests/test_data.py:6-31)
+    s = AudioMetricsData(False)
+    s.add(torch.from_numpy(ref[:5000])); s.add(torch.from_numpy(ref[5000:]))
+    np.testing.assert_allclose(s.cov.cpu().numpy(), tc.cov.cpu().numpy(), rtol=1e-7, atol=1e-12)
+
+
+# -------------------------------------------------------------------- Frechet paths
+def test_frechet_factor_paths_agree(cuda_device, monkeypatch):
+    ref, cand = make_sets_numpy(6000, 5000, 200, seed=4)
+    ref[:, 10] = ref[:, 11]                          # singular covariances with n >> d
+    cand[:, 10] = cand[:, 11]
+    ref[:, 12] = 0.0
+    A, B = _amd(cand, False), _amd(ref, False)
+    chol = frechet_distance(A, B)
+    monkeypatch.setenv("AMB_FAD_FACTOR", "eig")
+    eig = frechet_distance(A, B)
+    monkeypatch.delenv("AMB_FAD_FACTOR")
+    mx, cx = _stats64(cand); my, cy = _stats64(ref)
+    want = oracle.frechet_from_stats(mx, cx, my, cy)
+    assert chol == pytest.approx(want, rel=1e-5)
+    assert eig == pytest.approx(want, rel=1e-5)
+    assert chol == pytest.approx(eig, rel=1e-7)
+    for bs in ("16", "8", "4"):                      # Jacobi block sizes
+        monkeypatch.setenv("AMB_JACOBI_BS", bs)
+        assert frechet_distance(A, B) == pytest.approx(chol, rel=1e-10)
+
+
+# ------------------------------------------------------- full-size properties (BASELINE N)
+def test_full_size_properties(cuda_device):
+    """At 200k x 512 no CPU oracle can run; check what must hold for ANY correct
+    implementation: a set against itself, shard reassembly, and a planted neighbourhood."""
+    n, d, k = 200_000, 512, 5
+    ref, cand = make_sets_torch(n, n, d, device=cuda_device)
+    R = AudioMetricsData(True); R.embeddings = ref
+    same = prdc(R, R, k)
+    assert same["precision"] == 1.0 and same["recall"] == 1.0 and same["coverage"] == 1.0
+    assert same["density"] == pytest.approx(1.0, abs=1e-4)        # exactly k of k+1 inside, up to exact ties
+    S = AudioMetricsData(False); S.add(ref)
+    T = AudioMetricsData(False); T.add(ref)
+    assert abs(frechet_distance(S, T)) < 1e-9 * float(S.cov.trace())
+    # radii are distances to real rows: recompute 64 of them exactly from the k+1 nearest rows
+    r = R.get_radii(k)
+    rows = torch.arange(0, n, n // 64, device=cuda_device)[:64]
+    d2 = torch.cdist(ref[rows].double(), ref.double()) ** 2
+    exact = d2.kthvalue(k + 1, dim=1).values.sqrt().float()
+    torch.testing.assert_close(r[rows], exact, rtol=3e-7, atol=0)
+    # candidate = shifted copy: every reference row has its twin at distance |shift|
+    shift = torch.zeros(d, device=cuda_device); shift[0] = 1e-3
+    C = AudioMetricsData(True); C.embeddings = ref + shift
+    out = prdc(R, C, k)
+    assert out["coverage"] == 1.0 and out["precision"] == 1.0 and out["recall"] == 1.0
