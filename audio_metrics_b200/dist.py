@@ -94,7 +94,7 @@ class CudaOps:
         a, b = _S(), _S()
         a.mean, a.cov = sx
         b.mean, b.cov = sy
-        return frechet_distances([(a, b)], device=self.device)[0]
+        return frechet_distances([(a, b)], device=self.device, as_tensor=True)[0]   # stays on the device
 
     def container(self, x):
         from .data import AudioMetricsData
@@ -115,10 +115,13 @@ class CudaOps:
         col, rec, cov, totals = prdc_totals(cref, ccand, k, row_range=(row0, nrows), ref_radii=r_ref,
                                             cand_radii=r_cand)
         t = torch.stack([rec.sum(dtype=torch.int64), cov.sum(dtype=torch.int64), totals[4]])
-        cap = self._lib.lib().amb_prdc_list_cap(len(cref.embeddings), len(ccand.embeddings))
-        if int(t[2]) > cap:
-            raise self._lib.AmbError(f"{int(t[2])} near-tie pairs exceed the refine list capacity {cap}")
         return col, t
+
+    def check_uncertain(self, uncertain, n_ref, n_cand):
+        """The refine list has a fixed capacity; pairs beyond it were not re-decided."""
+        cap = self._lib.lib().amb_prdc_list_cap(n_ref, n_cand)
+        if uncertain > cap * max(1, _world(None)[0]):
+            raise self._lib.AmbError(f"{uncertain} near-tie pairs exceed the refine list capacity {cap}")
 
     def kd_mmds(self, f1, f2, idx, gamma, coef0, degree):
         L, dev = self._lib.lib(), self.device
@@ -137,67 +140,98 @@ class CudaOps:
 
 
 def evaluate_sharded(ref_shard, cand_shard, n_ref, n_cand, metrics=("fad", "kd", "prdc"), nearest_k=5,
-                     group=None, ops=None, kd_subsets=100, kd_subset_size=1000, kd_seed=1234):
+                     group=None, ops=None, kd_subsets=100, kd_subset_size=1000, kd_seed=1234, ready=None):
     """FAD / KD / PRDC of (reference, candidate) given this rank's row shards.
 
     ``ref_shard`` / ``cand_shard`` are this rank's rows per ``shard_rows``; every
     rank returns the same result dict (keys as AudioMetrics.evaluate,
     audio_metrics.py:254-274).  With an uninitialised process group this is the
     single-GPU path.
+
+    Everything is enqueued without a host synchronisation and read back once at the
+    end (the reference makes one ``.item()`` per metric): the KD subset indices are
+    drawn on the host (numpy, kd.py:176-186) while the GPU is busy with PRDC.
+    ``ready = (event_ref, event_cand)`` (CUDA events, either may be None) lets the caller
+    hand over shards whose host-to-device copies are still in flight on another stream:
+    all reference-only work (moments, packing, radii) is queued before the candidate
+    shard is first touched.
     """
     from .metrics.kd import draw_subset_indices, KID_DEGREE, KID_COEF0
 
     ops = ops or CudaOps()
     world, rank = _world(group)
     d = ref_shard.shape[1]
-    result = {}
     r_row0, r_nrows, r_chunk = shard_rows(n_ref, world, rank)
     c_row0, c_nrows, c_chunk = shard_rows(n_cand, world, rank)
     assert ref_shard.shape[0] == r_nrows and cand_shard.shape[0] == c_nrows, "shards must follow shard_rows()"
+    want_fad, want_kd, want_prdc = "fad" in metrics, "kd" in metrics, "prdc" in metrics
+    k = nearest_k
 
-    if "fad" in metrics:
-        mom = torch.cat([ops.moments(ref_shard), ops.moments(cand_shard)])
+    def wait(ev):
+        if ev is not None:
+            torch.cuda.current_stream(ref_shard.device).wait_event(ev)
+
+    ev_ref, ev_cand = ready if ready is not None else (None, None)
+    pending = {}                                     # device-side results, read back at the end
+
+    # ---- reference-only work
+    wait(ev_ref)
+    if want_fad:
+        mom_ref = ops.moments(ref_shard)
+    if want_kd or want_prdc:
+        ref = _allgather_rows(ref_shard, n_ref, r_chunk, group)
+    if want_prdc:
+        cref = ops.container(ref)
+        r_ref = _allgather_rows(ops.radii_rows(cref, r_row0, r_nrows, k), n_ref, r_chunk, group).contiguous()
+
+    # ---- candidate
+    wait(ev_cand)
+    if want_fad:
+        mom = torch.cat([mom_ref, ops.moments(cand_shard)])
         _allreduce(mom, group)                       # one message: 2 (d + d^2) doubles
         half = d + d * d
         s_ref = ops.stats_from_moments(mom[:half], n_ref, d)
         s_cand = ops.stats_from_moments(mom[half:], n_cand, d)
-        result["fad"] = ops.frechet(s_cand, s_ref)    # (cand, ref) as audio_metrics.py:257
-
-    if "kd" in metrics or "prdc" in metrics:
-        ref = _allgather_rows(ref_shard, n_ref, r_chunk, group)
+        pending["fad"] = ops.frechet(s_cand, s_ref)  # (cand, ref) as audio_metrics.py:257
+    if want_kd or want_prdc:
         cand = _allgather_rows(cand_shard, n_cand, c_chunk, group)
+    if want_prdc:
+        ccand = ops.container(cand)
+        r_cand = _allgather_rows(ops.radii_rows(ccand, c_row0, c_nrows, k), n_cand, c_chunk, group).contiguous()
+        col, t = ops.count_rows(cref, ccand, r_ref, r_cand, r_row0, r_nrows, k)
+        _allreduce(col, group)                       # [m] int32
+        _allreduce(t, group)                         # 3 int64
+        pending["prdc"] = torch.cat([torch.stack([(col > 0).sum(dtype=torch.int64), col.sum(dtype=torch.int64)]),
+                                     t.to(torch.int64)])
 
-    if "kd" in metrics:
+    if want_kd:
         n_s = min(n_ref, n_cand)
         m = kd_subset_size if kd_subset_size < n_s else max(1, n_s // 2)        # kd.py:160-168
         idx = draw_subset_indices(n_cand, n_ref, m, kd_subsets, kd_seed)         # features_1 = candidate
         mine = idx[rank::world]
         per = -(-kd_subsets // world)
         local = ops.kd_mmds(cand, ref, mine, 1.0 / d, KID_COEF0, KID_DEGREE)
-        pad = torch.zeros(per, dtype=torch.float64, device=local.device)
-        pad[: local.shape[0]] = local
         if world > 1:
+            pad = torch.zeros(per, dtype=torch.float64, device=local.device)
+            pad[: local.shape[0]] = local
             allv = torch.empty(world * per, dtype=torch.float64, device=local.device)
             dist.all_gather_into_tensor(allv, pad, group=group)
-            allv = allv.view(world, per)
-            mmds = torch.stack([allv[s % world, s // world] for s in range(kd_subsets)])
+            order = torch.tensor([(s % world) * per + s // world for s in range(kd_subsets)], device=local.device)
+            pending["kd"] = allv[order]
         else:
-            mmds = local
-        mm = mmds.cpu().numpy()
+            pending["kd"] = local
+
+    # ---- the one read-back
+    result = {}
+    if want_fad:
+        result["fad"] = float(pending["fad"])
+    if want_kd:
+        mm = pending["kd"].cpu().numpy()
         result["kernel_distance_mean"] = float(np.mean(mm))                       # kd.py:190
         result["kernel_distance_std"] = float(np.std(mm))                         # kd.py:191
-
-    if "prdc" in metrics:
-        k = nearest_k
-        cref, ccand = ops.container(ref), ops.container(cand)
-        r_ref = _allgather_rows(ops.radii_rows(cref, r_row0, r_nrows, k), n_ref, r_chunk, group).contiguous()
-        r_cand = _allgather_rows(ops.radii_rows(ccand, c_row0, c_nrows, k), n_cand, c_chunk, group).contiguous()
-        col, t = ops.count_rows(cref, ccand, r_ref, r_cand, r_row0, r_nrows, k)
-        _allreduce(col, group)                       # [m] int32
-        _allreduce(t, group)                         # 3 int64
-        hits = int((col > 0).sum())
-        total = int(col.sum(dtype=torch.int64))
-        recalled, covered, _ = t.tolist()
+    if want_prdc:
+        hits, total, recalled, covered, uncertain = pending["prdc"].tolist()
+        ops.check_uncertain(uncertain, n_ref, n_cand)
         result.update(precision=hits / n_cand, recall=recalled / n_ref,
                       density=(1.0 / float(k)) * (total / n_cand), coverage=covered / n_ref)   # prdc.py:36-48
     return result

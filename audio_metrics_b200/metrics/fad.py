@@ -6,11 +6,12 @@ import torch
 from .. import _lib
 
 
-def frechet_distances(pairs, device=None):
+def frechet_distances(pairs, device=None, as_tensor=False):
     """FAD for several (x, y) container pairs in one batched launch sequence.
 
     Each element of ``pairs`` is ``(x, y)`` with ``.mean`` / ``.cov`` attributes
-    (fad.py:8-13).  Returns a list of python floats.
+    (fad.py:8-13).  Returns a list of python floats, or with ``as_tensor`` the fp64
+    device tensor without synchronising.
     """
     dev = _lib.require_cuda(device if device is not None else pairs[0][0].mean.device
                             if isinstance(pairs[0][0].mean, torch.Tensor) and pairs[0][0].mean.is_cuda else None)
@@ -27,6 +28,8 @@ def frechet_distances(pairs, device=None):
     ws = _lib.workspace(L.amb_frechet_ws_bytes(batch, d), dev)
     _lib.check(L.amb_frechet(dev.index, _lib.stream_ptr(dev), batch, d, mu_x.data_ptr(), cov_x.data_ptr(),
                              mu_y.data_ptr(), cov_y.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel()))
+    if as_tensor:
+        return out
     return out.tolist()   # the one device->host read fad.py:13 (.item()) makes
 
 

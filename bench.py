@@ -215,9 +215,9 @@ def run_b200_arm(args):
     torch.cuda.empty_cache()
     pairs = workload_pairs(N_REF, N_CAND)
 
-    def step(rs, cs):
+    def step(rs, cs, ready=None):
         return evaluate_sharded(rs, cs, N_REF, N_CAND, metrics=("fad", "kd", "prdc"), nearest_k=K_NN,
-                                kd_subsets=KD_SUBSETS, kd_subset_size=KD_SUBSET_SIZE)
+                                kd_subsets=KD_SUBSETS, kd_subset_size=KD_SUBSET_SIZE, ready=ready)
 
     def barrier():
         if world > 1:
@@ -258,10 +258,21 @@ def run_b200_arm(args):
     ref_host = ref_shard.cpu().pin_memory()
     cand_host = cand_shard.cpu().pin_memory()
 
+    copy_stream = torch.cuda.Stream(dev)
+
     def e2e_step():
-        rs = ref_host.to(dev, non_blocking=True)
-        cs = cand_host.to(dev, non_blocking=True)
-        return step(rs, cs)
+        # the two H2D copies run on their own stream; evaluate_sharded queues all reference-only
+        # work behind the first copy and touches the candidate shard only after the second
+        main = torch.cuda.current_stream(dev)
+        copy_stream.wait_stream(main)
+        with torch.cuda.stream(copy_stream):
+            rs = ref_host.to(dev, non_blocking=True)
+            ev_r = torch.cuda.Event(); ev_r.record(copy_stream)
+            cs = cand_host.to(dev, non_blocking=True)
+            ev_c = torch.cuda.Event(); ev_c.record(copy_stream)
+        rs.record_stream(main)
+        cs.record_stream(main)
+        return step(rs, cs, ready=(ev_r, ev_c))
 
     e2e_step()
     ms_e2e, result_e2e = timed(e2e_step, max(1, min(args.steps, 3)))

@@ -39,6 +39,9 @@ class OracleOps:
         cov = (D < rr[:, None]).any(axis=1).sum()
         return torch.from_numpy(col), torch.tensor([int(rec), int(cov), 0], dtype=torch.int64)
 
+    def check_uncertain(self, uncertain, n_ref, n_cand):
+        assert uncertain == 0
+
     def kd_mmds(self, f1, f2, idx, gamma, coef0, degree):
         a, b = f1.numpy().astype(np.float64), f2.numpy().astype(np.float64)
         out = np.zeros(len(idx))
