@@ -135,8 +135,8 @@ jacobi_kernel(double* __restrict__ Gt, int d, int n_mat, double tol, int* __rest
 // jacobi_kernel; only the order of the pairs differs.
 template <int BS, int NR>
 __global__ void __launch_bounds__(32 * BS)
-jacobi_block_kernel(double* __restrict__ Gt, int d, int n_mat, double tol, int* __restrict__ rot_count,
-                    int* __restrict__ sweeps_done) {
+jacobi_block_kernel(double* __restrict__ Gt, int d, int n_mat, double tol, int stop_rot,
+                    int* __restrict__ rot_count, int* __restrict__ sweeps_done) {
   extern __shared__ double slab[];                 // [2*BS][d]
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
@@ -234,7 +234,10 @@ jacobi_block_kernel(double* __restrict__ Gt, int d, int n_mat, double tol, int* 
     }
     if (lane == 0 && my_rot) atomicAdd(&rot_count[sweep], my_rot);
     grid.sync();
-    if (*reinterpret_cast<volatile int*>(&rot_count[sweep]) == 0) { ++sweep; break; }
+    // Converged when a sweep rotated (almost) nothing: every pair it visited was below tol or
+    // was made orthogonal by its rotation, and the few rotations of such a sweep are by angles of
+    // the order of tol, so they re-mix the other columns only to second order.
+    if (*reinterpret_cast<volatile int*>(&rot_count[sweep]) <= stop_rot) { ++sweep; break; }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *sweeps_done = sweep;
 }
@@ -458,8 +461,8 @@ fad_combine_kernel(int d, const double* __restrict__ mu_x, const double* __restr
 }
 
 template <int BS, int NR>
-static int launch_jacobi_block(cudaStream_t st, int dev, double* Gt, int d, int n_mat, double tol, int* rot,
-                               int* sweeps) {
+static int launch_jacobi_block(cudaStream_t st, int dev, double* Gt, int d, int n_mat, double tol, int stop_rot,
+                               int* rot, int* sweeps) {
   const size_t smem = static_cast<size_t>(2) * BS * d * sizeof(double);
   auto* fn = jacobi_block_kernel<BS, NR>;
   int rc = check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
@@ -473,7 +476,7 @@ static int launch_jacobi_block(cudaStream_t st, int dev, double* Gt, int d, int 
   long long want = static_cast<long long>(nb / 2) * n_mat;
   const long long cap = static_cast<long long>(per_sm) * sm_count(dev);
   if (want > cap) want = cap;
-  void* args[] = {&Gt, &d, &n_mat, &tol, &rot, &sweeps};
+  void* args[] = {&Gt, &d, &n_mat, &tol, &stop_rot, &rot, &sweeps};
   rc = check_cuda(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fn), dim3(static_cast<unsigned>(want)),
                                               dim3(32 * BS), args, smem, st),
                   "cudaLaunchCooperativeKernel(jacobi_block_kernel)");
@@ -481,8 +484,15 @@ static int launch_jacobi_block(cudaStream_t st, int dev, double* Gt, int d, int 
   return check_launch("jacobi_block_kernel");
 }
 
-static int launch_jacobi(cudaStream_t st, int dev, double* Gt, int d, int n_mat, int* counters) {
-  double tol = 1e-14;
+// `values_only`: the caller needs the singular values (column norms) but not the rotated
+// columns themselves.  The sum of the column norms is stationary at convergence — its error is
+// second order in the remaining cosines (for two columns (|a|+|b|)^2 - (s1+s2)^2 = 2|a||b|(1 - sqrt(1-c^2)))
+// — so cosines below 1e-8 leave it exact to fp64 round-off, and the sweep that only confirms
+// convergence can be dropped.  Eigen-FACTORS (the AMB_FAD_FACTOR=eig path) are first order in the
+// cosines and keep the 1e-14 test and the confirming sweep.
+static int launch_jacobi(cudaStream_t st, int dev, double* Gt, int d, int n_mat, int* counters, bool values_only) {
+  double tol = values_only ? 1e-8 : 1e-14;
+  int stop_rot = values_only ? d / 8 : 0;
   int* rot = counters;
   int* sweeps = counters + kJacobiMaxSweeps;
   int rc = check_cuda(cudaMemsetAsync(counters, 0, (kJacobiMaxSweeps + 1) * sizeof(int), st), "memset");
@@ -501,9 +511,9 @@ static int launch_jacobi(cudaStream_t st, int dev, double* Gt, int d, int n_mat,
       if (v == 4 || v == 8 || v == 16) bs = v;
     }
 #define AMB_JB(BS)                                                                                   \
-    (d <= 128 ? launch_jacobi_block<BS, 4>(st, dev, Gt, d, n_mat, tol, rot, sweeps)                    \
-     : d <= 256 ? launch_jacobi_block<BS, 8>(st, dev, Gt, d, n_mat, tol, rot, sweeps)                  \
-                : launch_jacobi_block<BS, 16>(st, dev, Gt, d, n_mat, tol, rot, sweeps))
+    (d <= 128 ? launch_jacobi_block<BS, 4>(st, dev, Gt, d, n_mat, tol, stop_rot, rot, sweeps)                    \
+     : d <= 256 ? launch_jacobi_block<BS, 8>(st, dev, Gt, d, n_mat, tol, stop_rot, rot, sweeps)                  \
+                : launch_jacobi_block<BS, 16>(st, dev, Gt, d, n_mat, tol, stop_rot, rot, sweeps))
     if (bs == 16) return AMB_JB(16);
     if (bs == 8) return AMB_JB(8);
     return AMB_JB(4);
@@ -568,7 +578,7 @@ int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu
   const char* mode = getenv("AMB_FAD_FACTOR");   // "eig": eigen-factors by Jacobi (the slower first implementation)
   double* F = Lt;
   if (mode && mode[0] == 'e') {
-    if ((rc = launch_jacobi(st, dev, G, d, 2 * batch, counters))) return rc;
+    if ((rc = launch_jacobi(st, dev, G, d, 2 * batch, counters, false))) return rc;
     factor_scale_kernel<<<(2 * batch * d * 32 + 255) / 256, 256, 0, st>>>(G, d, 2 * batch);
     if ((rc = check_launch("factor_scale_kernel"))) return rc;
     F = G;
@@ -599,7 +609,7 @@ int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu
   dim3 ggrid((d + 63) / 64, (d + 63) / 64, batch);
   dgemm_nt_kernel<<<ggrid, 256, 0, st>>>(F, F + batch * mat, Mt, d);   // Mt[i][j] = <F_x col i, F_y col j>
   if ((rc = check_launch("dgemm_nt_kernel"))) return rc;
-  if ((rc = launch_jacobi(st, dev, Mt, d, batch, counters + 64))) return rc;
+  if ((rc = launch_jacobi(st, dev, Mt, d, batch, counters + 64, true))) return rc;
   fad_combine_kernel<<<batch, 256, 0, st>>>(d, mu_x, cov_x, mu_y, cov_y, Mt, out);
   if ((rc = check_launch("fad_combine_kernel"))) return rc;
   if (getenv("AMB_FAD_DEBUG")) {   // ranks, sweeps / rotations per sweep of the Jacobi stages (synchronises)
