@@ -203,6 +203,11 @@ int amb_debug_dot_matrix(int dev, amb_stream_t stream, const void* packed_a, lon
   DumpEpi epi{a.inv_scale, b.inv_scale, C, ldc, na, nb, ldc == 0 ? 1 : 0};
   // AMB_DEBUG_SINGLE=1: hi planes only through the single-pass kernel (11-bit operands)
   const char* e = getenv("AMB_DEBUG_SINGLE");
+  if (e && atoi(e) == 2 && g.kb_count <= kMaxResidentKb) {   // ... on CTA pairs (cta_group::2)
+    g.n_rt /= 2;                                             // rows_pad is a multiple of 256
+    return launch_engine2(static_cast<cudaStream_t>(stream), dev, g, epi, "pair_engine2<dump>",
+                          static_cast<double>(na) * nb);
+  }
   if (e && atoi(e) == 1 && g.kb_count <= kMaxResidentKb)
     return launch_engine1(static_cast<cudaStream_t>(stream), dev, g, epi, "pair_engine1<dump>",
                           static_cast<double>(na) * nb);

@@ -5,6 +5,7 @@
 #include <mutex>
 
 #include "epilogues.cuh"
+#include "pair_engine2.cuh"
 #include "internal.cuh"
 
 namespace amb {
@@ -67,6 +68,40 @@ int launch_engine1(cudaStream_t stream, int dev, EngineGeom g, const Epi& epi, c
                             (g.kb_count * static_cast<double>(kBlockK));
   void* tok = profile_begin(stream);
   pair_engine1_kernel<Epi><<<grid, kEngineThreads, smem, stream>>>(g, epi);
+  profile_end(tok, stream, alg_pairs, exec_flops);
+  return check_launch(what);
+}
+
+// Two-CTA variant (pair_engine2_kernel): g.n_rt counts row-tile PAIRS.
+template <class Epi>
+int launch_engine2(cudaStream_t stream, int dev, EngineGeom g, const Epi& epi, const char* what,
+                   double alg_pairs = 0.0) {
+  if (g.kb_count > kMaxResidentKb) return set_error(AMB_ERR_ARG, "%s: kb_count %d too large for the resident panel", what, g.kb_count);
+  const size_t fixed = size_t(g.kb_count) * kChunkBytes + sizeof(EngineSmem2Of<Epi>) + (Epi::kScratch ? kScratchBytes : 0);
+  int n_stages = static_cast<int>((kMaxDynSmem - fixed) / kStage2Bytes);
+  if (n_stages > kMaxStages) n_stages = kMaxStages;
+  if (const char* e = getenv("AMB_STAGES")) {
+    const int v = atoi(e);
+    if (v >= 2 && v < n_stages) n_stages = v;
+  }
+  if (n_stages < 2) return set_error(AMB_ERR_ARG, "%s: shared memory too small for the B ring", what);
+  g.n_stages = n_stages;
+  const size_t smem = fixed + size_t(n_stages) * kStage2Bytes;
+  cudaError_t attr_err = cudaFuncSetAttribute(pair_engine2_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(kMaxDynSmem));
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(pair_engine2)");
+  const long long items = static_cast<long long>(g.n_problems) * g.n_rt * g.n_split;
+  if (items <= 0) return AMB_OK;
+  int pairs = sm_count(dev) / 2;
+  if (const char* e = getenv("AMB_GRID")) {
+    const int v = atoi(e) / 2;
+    if (v >= 1 && v < pairs) pairs = v;
+  }
+  const unsigned grid = 2u * static_cast<unsigned>(items < pairs ? items : pairs);
+  const double exec_flops = static_cast<double>(g.n_problems) * g.n_rt * g.n_ct * (2.0 * 2 * kTileM * kTileN) *
+                            (g.kb_count * static_cast<double>(kBlockK));
+  void* tok = profile_begin(stream);
+  pair_engine2_kernel<Epi><<<grid, kEngineThreads, smem, stream>>>(g, epi);   // __cluster_dims__(2,1,1)
   profile_end(tok, stream, alg_pairs, exec_flops);
   return check_launch(what);
 }

@@ -345,7 +345,7 @@ struct KnnWs {
   size_t bytes;
 };
 static KnnWs knn_ws(void* ws, long long nrows, int Kt, int n_split) {
-  const long long list_rows = round_up_ll(nrows, kTileM);
+  const long long list_rows = round_up_ll(nrows, 2 * kTileM);   // the two-CTA engine works on row-tile pairs
   uint8_t* b = static_cast<uint8_t*>(ws);
   size_t off = 0;
   KnnWs w;
@@ -360,20 +360,32 @@ static KnnWs knn_ws(void* ws, long long nrows, int Kt, int n_split) {
   return w;
 }
 
-template <int K>
-static int run_topk(cudaStream_t st, int dev, EngineGeom& g, const PackedPtrs& p, const KnnWs& w,
-                    long long list_rows, long long a_row_base, double alg_pairs, bool single_pass) {
-  TopkEpi<K> epi{p.inv_scale, p.inv_scale, p.norm, w.keys, w.cols, list_rows, a_row_base};
-  if (single_pass) return launch_engine1(st, dev, g, epi, "pair_engine1<topk>", alg_pairs);
-  return launch_engine(st, dev, g, epi, "pair_engine<topk>", alg_pairs);
+// Engine choice for the filter sweeps: 3 = three-MMA split precision (any d), 1 = single MMA per
+// product with a resident A panel (d <= 512), 2 = the same on CTA pairs (cta_group::2).
+static int engine_mode(int kb_count, long long row0) {
+  if (kb_count > kMaxResidentKb) return 3;
+  const char* e = getenv("AMB_PASSES");
+  if (e && atoi(e) == 3) return 3;
+  const char* c = getenv("AMB_CTA2");   // AMB_CTA2=0: single-CTA kernel
+  const bool two = c ? atoi(c) != 0 : true;
+  // the pair kernel takes A row tiles two at a time: the shard must start on an even tile
+  return (two && (row0 / kTileM) % 2 == 0) ? 2 : 1;
 }
 
-// The filter runs as ONE fp16 MMA per product (hi planes) whenever the A row panel fits
-// in shared memory (d <= 512); AMB_PASSES=3 forces the three-MMA split-precision sweep.
-static bool use_single_pass(int kb_count) {
-  if (kb_count > kMaxResidentKb) return false;
-  const char* e = getenv("AMB_PASSES");
-  return !(e && atoi(e) == 3);
+template <class Epi>
+static int run_engine(int mode, cudaStream_t st, int dev, EngineGeom g, const Epi& epi, const char* what,
+                      double alg_pairs) {
+  if (mode == 3) return launch_engine(st, dev, g, epi, what, alg_pairs);
+  if (mode == 1) return launch_engine1(st, dev, g, epi, what, alg_pairs);
+  g.n_rt = (g.n_rt + 1) / 2;   // row-tile pairs
+  return launch_engine2(st, dev, g, epi, what, alg_pairs);
+}
+
+template <int K>
+static int run_topk(cudaStream_t st, int dev, EngineGeom& g, const PackedPtrs& p, const KnnWs& w,
+                    long long list_rows, long long a_row_base, double alg_pairs, int mode) {
+  TopkEpi<K> epi{p.inv_scale, p.inv_scale, p.norm, w.keys, w.cols, list_rows, a_row_base};
+  return run_engine(mode, st, dev, g, epi, "pair_engine<topk>", alg_pairs);
 }
 
 }  // namespace amb
@@ -419,12 +431,13 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
   }
   KnnWs w = knn_ws(ws, nrows, Kt, n_split);
   if (!ws || ws_bytes < w.bytes) return set_error(AMB_ERR_WS, "amb_knn_radii: workspace %zu < %zu", ws_bytes, w.bytes);
-  const long long list_rows = round_up_ll(nrows, kTileM);
+  const long long list_rows = round_up_ll(nrows, 2 * kTileM);
   int rc = check_cuda(cudaMemsetAsync(w.n_unresolved, 0, 512, st), "memset");   // n_unresolved + max_norm
   if (rc) return rc;
   max_norm_kernel<<<64, 256, 0, st>>>(p.norm, p.rho, p.rows_pad, w.max_norm);
   if ((rc = check_launch("max_norm_kernel"))) return rc;
-  const bool sp = use_single_pass(p.kb_count);
+  const int mode = engine_mode(p.kb_count, row0);
+  const bool sp = mode != 3;
 
   EngineGeom g{};
   g.a_planes = p.planes;
@@ -440,11 +453,11 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
   g.lbo_bytes = 128;
   g.sbo_bytes = 512;
   const double alg_pairs = static_cast<double>(nrows) * n;
-  if (Kt == 8) rc = run_topk<8>(st, dev, g, p, w, list_rows, row0, alg_pairs, sp);
-  else if (Kt == 12) rc = run_topk<12>(st, dev, g, p, w, list_rows, row0, alg_pairs, sp);
-  else if (Kt == 16) rc = run_topk<16>(st, dev, g, p, w, list_rows, row0, alg_pairs, sp);
-  else if (Kt == 24) rc = run_topk<24>(st, dev, g, p, w, list_rows, row0, alg_pairs, sp);
-  else rc = run_topk<32>(st, dev, g, p, w, list_rows, row0, alg_pairs, sp);
+  if (Kt == 8) rc = run_topk<8>(st, dev, g, p, w, list_rows, row0, alg_pairs, mode);
+  else if (Kt == 12) rc = run_topk<12>(st, dev, g, p, w, list_rows, row0, alg_pairs, mode);
+  else if (Kt == 16) rc = run_topk<16>(st, dev, g, p, w, list_rows, row0, alg_pairs, mode);
+  else if (Kt == 24) rc = run_topk<24>(st, dev, g, p, w, list_rows, row0, alg_pairs, mode);
+  else rc = run_topk<32>(st, dev, g, p, w, list_rows, row0, alg_pairs, mode);
   if (rc) return rc;
 
   const unsigned blocks = static_cast<unsigned>((nrows * 32 + 255) / 256);
@@ -519,7 +532,8 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   if ((rc = check_cuda(cudaMemsetAsync(q, 0, 512, st), "memset"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(row_recall, 0, nrows, st), "memset"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(row_cover, 0, nrows, st), "memset"))) return rc;
-  const bool sp = use_single_pass(pr.kb_count);
+  const int mode = engine_mode(pr.kb_count, row0);
+  const bool sp = mode != 3;
   max_norm_kernel<<<64, 256, 0, st>>>(pr.norm, pr.rho, pr.rows_pad, max_ref);
   if ((rc = check_launch("max_norm_kernel"))) return rc;
   max_norm_kernel<<<64, 256, 0, st>>>(pc.norm, pc.rho, pc.rows_pad, max_cand);
@@ -551,9 +565,7 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   g.sbo_bytes = 512;
   CountEpi epi{pr.inv_scale, pr.norm, a_lo, a_hi, pc.inv_scale, pc.norm, b_lo, b_hi, col_count, row_recall,
                row_cover, row0, row0 + nrows, list, list_count, static_cast<unsigned long long>(cap)};
-  rc = sp ? launch_engine1(st, dev, g, epi, "pair_engine1<count>", static_cast<double>(nrows) * m)
-          : launch_engine(st, dev, g, epi, "pair_engine<count>", static_cast<double>(nrows) * m);
-  if (rc) return rc;
+  if ((rc = run_engine(mode, st, dev, g, epi, "pair_engine<count>", static_cast<double>(nrows) * m))) return rc;
 
   const int blocks = 8 * sm_count(dev);
   if (dtype == AMB_F32)

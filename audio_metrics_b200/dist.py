@@ -9,7 +9,7 @@ row-independent, so the only exchanges are:
   counts       allreduce(sum) of the per-candidate counts and of two row totals
   KD           subsets dealt round-robin to ranks, allgather of the 100 MMD values
 
-Row shards are contiguous and aligned to 128 rows (the tensor-core row tile).
+Row shards are contiguous and aligned to 256 rows (two tensor-core row tiles).
 The arithmetic is delegated to an ``ops`` object so that the sharding and
 reduction logic can be exercised on CPU (gloo, world_size 2) in the test-suite
 with stand-in kernels; the product ``CudaOps`` calls the C ABI and nothing else.
@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROW_ALIGN = 128
+ROW_ALIGN = 256     # two row tiles: shards start on an even tile, so the CTA-pair engine applies
 
 
 def shard_rows(n: int, world: int, rank: int):

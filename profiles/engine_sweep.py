@@ -32,7 +32,7 @@ def child(n, d):
     rad = t(radii)
     flops = 2.0 * n * n * d
     print(f"passes={os.environ.get('AMB_PASSES','1')} single_dump={os.environ.get('AMB_DEBUG_SINGLE','0')} "
-          f"stages={os.environ.get('AMB_STAGES','max')} grid={os.environ.get('AMB_GRID','sms')} n={n} d={d}: checksum {dump:.2f} ms ({flops/dump/1e9:.0f} TF alg), "
+          f"cta2={os.environ.get('AMB_CTA2','0')} stages={os.environ.get('AMB_STAGES','max')} grid={os.environ.get('AMB_GRID','sms')} n={n} d={d}: checksum {dump:.2f} ms ({flops/dump/1e9:.0f} TF alg), "
           f"radii {rad:.2f} ms ({flops/rad/1e9:.0f} TF alg)", flush=True)
 
 if __name__ == "__main__":
@@ -43,6 +43,9 @@ if __name__ == "__main__":
     d = int(sys.argv[2]) if len(sys.argv) > 2 else 512
     if os.environ.get("AMB_SWEEP") == "grid":     # power-limit probe: fewer persistent CTAs than SMs
         configs = [dict(AMB_PASSES="1", AMB_DEBUG_SINGLE="1", AMB_GRID=g) for g in ("148", "111", "74", "37")]
+    elif os.environ.get("AMB_SWEEP") == "cta2":   # single-CTA vs CTA-pair engine
+        configs = [dict(AMB_PASSES="1", AMB_DEBUG_SINGLE="1", AMB_CTA2="0"),
+                   dict(AMB_PASSES="1", AMB_DEBUG_SINGLE="2", AMB_CTA2="1")]
     else:
         configs = [dict(AMB_PASSES="3", AMB_DEBUG_SINGLE="0")]
         for st in ("2", "3", "4", "5", "6", "8"):

@@ -37,16 +37,18 @@ def _stats64(x):
 def test_single_pass_and_split_sweeps_agree(cuda_device, monkeypatch, n, m, d, k):
     ref, cand = make_sets_numpy(n, m, d, seed=n + d + k)
     out = {}
-    for passes in ("1", "3"):
+    for name, passes, cta2 in (("pair", "1", "1"), ("single", "1", "0"), ("split", "3", "0")):
         monkeypatch.setenv("AMB_PASSES", passes)
+        monkeypatch.setenv("AMB_CTA2", cta2)
         R, C = _amd(ref), _amd(cand)
         r_ref = nearest_neighbour_distances(R, k)
         col, rec, cov, tot = prdc_totals(R, C, k)
-        out[passes] = (r_ref.cpu().numpy(), col.cpu().numpy(), rec.cpu().numpy(), cov.cpu().numpy(), int(tot[4]))
-    for a, b in zip(out["1"][:4], out["3"][:4]):
-        assert np.array_equal(a, b)
+        out[name] = (r_ref.cpu().numpy(), col.cpu().numpy(), rec.cpu().numpy(), cov.cpu().numpy(), int(tot[4]))
+    for other in ("single", "split"):
+        for a, b in zip(out["pair"][:4], out[other][:4]):
+            assert np.array_equal(a, b)
     # the single-pass band is wider: more pairs go through the exact refine
-    assert out["1"][4] >= out["3"][4]
+    assert out["pair"][4] == out["single"][4] >= out["split"][4]
 
 
 def test_wide_embeddings_use_the_split_sweep(cuda_device):
