@@ -1,7 +1,8 @@
 // Epilogue functors for the pair engine (see the concept in pair_engine.cuh).
 // Thread = one row of the 128 x 256 tile; `acc` holds 32 consecutive columns of
 // that row as raw fp32 bits.  acc * inv_scale_a[row] * inv_scale_b[col] is the
-// dot product <x_row, y_col>.
+// dot product <x_row, y_col>; inv_scale_b is the same for all 256 columns of a tile
+// (pack.cu scales per tile), so column vector 0 is read once per chunk.
 #pragma once
 #include "internal.cuh"
 #include "pair_engine.cuh"
@@ -31,14 +32,15 @@ struct DumpEpi {
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
                         long long b_row0, float*) const {
     if (r.a_row >= na) return;
+    const float sc = cv[0][c0] * r.isr;
     if (checksum_only) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) r.sum += f32(acc[j]) * cv[0][c0 + j] * r.isr;
+      for (int j = 0; j < 32; ++j) r.sum += f32(acc[j]) * sc;
       return;
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      if (b_row0 + j < nb) C[r.a_row * ldc + b_row0 + j] = f32(acc[j]) * cv[0][c0 + j] * r.isr;
+      if (b_row0 + j < nb) C[r.a_row * ldc + b_row0 + j] = f32(acc[j]) * sc;
     }
   }
   __device__ void row_end(Row& r, const ItemCoord&, int, long long, int, int, int) const {
@@ -95,10 +97,11 @@ struct KdEpi {
     const bool edge = (col0 + 32 > m_valid) || (r.sym && col0 <= r.row_in_problem && r.row_in_problem < col0 + 32);
     if (!edge && kernel_type == AMB_KERNEL_POLY && degree == 3) {
       double s0 = 0, s1 = 0;
+      const double g2 = r.gr * static_cast<double>(cv[0][c0]);   // powers of two: exact
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        const double u0 = fma(static_cast<double>(f32(acc[j]) * cv[0][c0 + j]), r.gr, coef0);
-        const double u1 = fma(static_cast<double>(f32(acc[j + 1]) * cv[0][c0 + j + 1]), r.gr, coef0);
+        const double u0 = fma(static_cast<double>(f32(acc[j])), g2, coef0);
+        const double u1 = fma(static_cast<double>(f32(acc[j + 1])), g2, coef0);
         s0 = fma(u0 * u0, u0, s0);
         s1 = fma(u1 * u1, u1, s1);
       }
@@ -189,12 +192,13 @@ struct TopkEpi {
     // K-th smallest key
     float t[32];
     float m0 = kInf, m1 = kInf, m2 = kInf, m3 = kInf;
+    const float sc = cv[0][c0] * r.m2isr;   // -2 / (scale_a scale_b): one per tile (powers of two, exact)
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      t[j + 0] = fmaf(f32(acc[j + 0]) * cv[0][c0 + j + 0], r.m2isr, cv[1][c0 + j + 0]);
-      t[j + 1] = fmaf(f32(acc[j + 1]) * cv[0][c0 + j + 1], r.m2isr, cv[1][c0 + j + 1]);
-      t[j + 2] = fmaf(f32(acc[j + 2]) * cv[0][c0 + j + 2], r.m2isr, cv[1][c0 + j + 2]);
-      t[j + 3] = fmaf(f32(acc[j + 3]) * cv[0][c0 + j + 3], r.m2isr, cv[1][c0 + j + 3]);
+      t[j + 0] = fmaf(f32(acc[j + 0]), sc, cv[1][c0 + j + 0]);
+      t[j + 1] = fmaf(f32(acc[j + 1]), sc, cv[1][c0 + j + 1]);
+      t[j + 2] = fmaf(f32(acc[j + 2]), sc, cv[1][c0 + j + 2]);
+      t[j + 3] = fmaf(f32(acc[j + 3]), sc, cv[1][c0 + j + 3]);
       m0 = fminf(m0, t[j + 0]);
       m1 = fminf(m1, t[j + 1]);
       m2 = fminf(m2, t[j + 2]);
@@ -299,11 +303,11 @@ struct CountEpi {
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
                         long long b_row0, float*) const {
     bool any_ref = false, any_cand = false;
+    const float sc = cv[0][c0] * r.m2isr;   // -2 / (scale_a scale_b): one per tile (powers of two, exact)
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float q = f32(acc[j]) * cv[0][c0 + j];
-      const float t = fmaf(q, r.m2isr, cv[1][c0 + j]);
-      const float u = fmaf(q, r.m2isr, r.nx);
+      const float t = fmaf(f32(acc[j]), sc, cv[1][c0 + j]);
+      const float u = fmaf(f32(acc[j]), sc, r.nx);
       any_ref |= (t < r.Ahi);
       any_cand |= (u < cv[2][c0 + j]);
     }
@@ -314,7 +318,7 @@ struct CountEpi {
       unsigned m_hi = 0, m_lo = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float t = fmaf(f32(acc[j]) * cv[0][c0 + j], r.m2isr, cv[1][c0 + j]);
+        const float t = fmaf(f32(acc[j]), sc, cv[1][c0 + j]);
         m_hi |= (t < r.Ahi) ? (1u << j) : 0u;
         m_lo |= (t < r.Alo) ? (1u << j) : 0u;
       }
@@ -335,7 +339,7 @@ struct CountEpi {
       unsigned m_hi = 0, m_lo = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float u = fmaf(f32(acc[j]) * cv[0][c0 + j], r.m2isr, r.nx);
+        const float u = fmaf(f32(acc[j]), sc, r.nx);
         m_hi |= (u < cv[2][c0 + j]) ? (1u << j) : 0u;
         m_lo |= (u < cv[3][c0 + j]) ? (1u << j) : 0u;
       }

@@ -32,13 +32,13 @@ int sm_count(int dev);
 void* profile_begin(cudaStream_t stream);
 void profile_end(void* token, cudaStream_t stream, double alg_pairs, double exec_flops);
 
-// Layout of a packed blob (see packed.cuh): [hi plane][lo plane][inv_scale][norm][rho].
+// Layout of a packed blob (see packed.cuh): [hi plane][lo plane][inv_scale][norm][rho][row_exp].
 struct PackedLayout {
   long long rows_pad;
   int kpad;
   int kb_count;
   long long plane_halfs;
-  size_t off_lo, off_inv, off_norm, off_rho, bytes;
+  size_t off_lo, off_inv, off_norm, off_rho, off_exp, bytes;
 };
 PackedLayout packed_layout(long long n_rows, int d);
 
@@ -48,6 +48,7 @@ struct PackedPtrs {
   float* inv_scale;
   float* norm;
   float* rho;   // |x - hi(x)|, rounded up: what the single-pass filter's error band is built from
+  int* row_exp; // binary exponent of each row's largest magnitude (scratch of the pack pass)
   long long rows_pad;
   int kb_count;
 };
@@ -56,7 +57,7 @@ PackedPtrs packed_ptrs(void* blob, long long n_rows, int d);
 int launch_pack(cudaStream_t stream, const void* src, int dtype, long long ld, int d,
                 long long n_src_rows, const int* gather, long long n_valid, long long row0,
                 long long n_rows_out, __half* planes, long long plane_halfs, int kb_count,
-                float* inv_scale, float* norm, float* rho);
+                float* inv_scale, float* norm, float* rho, int* row_exp);
 
 // Integer tensor-core Gram / column sums of an fp32 matrix (cov_tc.cu).
 size_t cov_tc_ws_bytes(long long n, int d);

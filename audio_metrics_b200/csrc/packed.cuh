@@ -2,8 +2,9 @@
 //
 // An embedding matrix X [n, d] (fp32 or fp64, row-major) is rewritten once per
 // set into two fp16 planes  hi, lo  with  x * 2^e_row  ~=  hi + lo  (22+ bits of
-// the scaled value; e_row is a per-row power of two putting the row's largest
-// magnitude in [2^14, 2^15) so that neither plane under- or overflows fp16).
+// the scaled value; e_row is a power of two SHARED BY THE 256 ROWS OF A TILE that puts
+// the tile's largest magnitude in [2^14, 2^15) so that neither plane overflows fp16;
+// fp16's 30 binades keep rows far below the tile maximum at full precision).
 // The planes are stored in HBM already in the shared-memory image the tensor
 // core reads (K-major, no swizzle, 8-row x 16-byte core matrices), so that one
 // pipeline stage is a handful of contiguous 8 KiB bulk copies and needs no
