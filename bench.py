@@ -300,7 +300,7 @@ def run_b200_arm(args):
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops"], "traffic": load_traffic(),
-        "kernel": "pair_engine1_kernel<TopkEpi|CountEpi> (tcgen05 kind::f16, one MMA per product, A panel resident in smem) + pair_engine_kernel<KdEpi> (3-MMA split)",
+        "kernel": "pair_engine2_kernel<TopkEpi|CountEpi> (tcgen05 kind::f16 cta_group::2, one MMA per product, A panels resident in smem) + pair_engine_kernel<KdEpi> (3-MMA split)",
         "launches_timed": int(eng_launches), "avg_launch_ms": eng_ms / eng_launches if eng_launches else None,
         "kernel_share_of_step": eng_ms / (ms_step * args.steps) if ms_step > 0 else None,
         "executed_tflops": executed, "executed_frac": executed / peaks["tflops"], "peak_source": peaks["source"],
