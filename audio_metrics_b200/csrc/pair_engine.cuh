@@ -56,6 +56,7 @@ struct EngineGeom {
   uint32_t lbo_bytes;
   uint32_t sbo_bytes;
   int n_stages;              // single-pass kernel: B ring depth chosen by the host (<= kMaxStages)
+  int* work_counter;         // CTA-pair kernel: zeroed device counter for dynamic item hand-out (nullptr: static)
 };
 
 constexpr int kMaxStages = 8;

@@ -18,12 +18,21 @@
 //   tmem_full[acc]     local   L's MMA commit, multicast: accumulator acc is complete
 //   tmem_empty[acc]    local   this CTA's 8 epilogue warps drained acc (gates the column-vector copies)
 //   pair_tmem_empty[acc] in L  all 16 epilogue warps of the pair drained acc (gates L's next MMAs)
+//
+// Work items are handed out DYNAMICALLY (g.work_counter != nullptr): the leader's producer warp
+// takes the next item with one atomicAdd, publishes it in a two-slot mailbox in both CTAs
+// (sched_item / sched_full) and every other warp of the pair reads it there and acknowledges on
+// the leader's sched_empty.  A CTA pair that gets its SMs late (another kernel — the N-independent
+// FAD kernels on a second stream — was holding them) simply takes fewer items, and the last wave
+// balances itself.
 #pragma once
 #include "pair_engine.cuh"
 
 namespace amb {
 
 constexpr int kStage2Bytes = 2 * kChunkBytes;            // this CTA's B half, two k blocks (K = 64)
+constexpr int kSchedSlots = 2;
+constexpr int kSchedConsumers = 2 * (kEngineThreads / 32) - 1;   // every warp of the pair but the scheduler
 
 template <int NCV>
 struct EngineSmem2T {
@@ -38,6 +47,9 @@ struct EngineSmem2T {
   uint64_t a_full;
   uint64_t peer_a_full;
   uint64_t a_empty;
+  uint64_t sched_full[kSchedSlots];    // mailbox slot written (both CTAs)
+  uint64_t sched_empty[kSchedSlots];   // in L: all other warps of the pair have read the slot
+  int sched_item[kSchedSlots];
   uint32_t tmem_base;
   uint32_t pad_;
 };
@@ -69,6 +81,59 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 // wait on a local barrier whose arrivals come from the other CTA: the plain .acquire.cta wait
 // (an .acquire.cluster wait is followed by CCTL.IVALL, an L1 invalidate, on every probe)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+// Cluster-scope release / acquire pair for the item mailbox (generic-proxy data crosses CTAs
+// here, once per work item, so the full fences are the right tool and their cost is irrelevant).
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins == (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void st_cluster_s32(uint32_t cluster_addr, int v) {
+  asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+
+// Next work item of this CTA pair.  `it` counts the items this warp has asked for.
+//   scheduler = warp 0 of the leader CTA; every other warp of the pair is a consumer.
+template <class SM>
+__device__ __forceinline__ int next_item(SM* sh, const EngineGeom& g, int& it, int cluster_id, int n_clusters,
+                                         bool scheduler, int lane) {
+  if (g.work_counter == nullptr) return cluster_id + (it++) * n_clusters;   // static round robin
+  const int slot = it & (kSchedSlots - 1);
+  const uint32_t par = static_cast<uint32_t>(it / kSchedSlots) & 1u;
+  ++it;
+  int item = 0;
+  if (scheduler) {
+    mbar_wait(&sh->sched_empty[slot], par ^ 1u);
+    if (lane == 0) {
+      item = atomicAdd(g.work_counter, 1);
+      sh->sched_item[slot] = item;
+      st_cluster_s32(map_to_cta(&sh->sched_item[slot], 1), item);
+      mbar_arrive(&sh->sched_full[slot]);
+      mbar_arrive_release_cluster(map_to_cta(&sh->sched_full[slot], 1));
+    }
+    item = __shfl_sync(0xffffffffu, item, 0);
+  } else {
+    mbar_wait_acquire_cluster(&sh->sched_full[slot], par);
+    item = *reinterpret_cast<volatile int*>(&sh->sched_item[slot]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(map_to_cta(&sh->sched_empty[slot], 0));
+  }
+  return item;
+}
+
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
                "r"(ncols)
@@ -135,6 +200,10 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
     mbar_init(&sh->a_full, 1);
     mbar_init(&sh->peer_a_full, 1);
     mbar_init(&sh->a_empty, 1);
+    for (int q = 0; q < kSchedSlots; ++q) {
+      mbar_init(&sh->sched_full[q], 1);
+      mbar_init(&sh->sched_empty[q], kSchedConsumers);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -152,7 +221,10 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
     uint32_t ph = 0, a_ph = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int item = cluster_id; item < n_items; item += n_clusters) {
+    int it = 0;
+    for (;;) {
+      const int item = next_item(sh, g, it, cluster_id, n_clusters, leader, lane);
+      if (item >= n_items) break;
       const ItemCoord c = decode_item(g, item);
       const long long a_rb = (g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + 2ll * c.rt + rank;
       const long long b_rb_base = (g.b_rb0 ? g.b_rb0[c.problem] : 0) + g.b_rb_base;
@@ -200,7 +272,10 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
       uint32_t ph = 0, a_ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int item = cluster_id; item < n_items; item += n_clusters) {
+      int it = 0;
+      for (;;) {
+        const int item = next_item(sh, g, it, cluster_id, n_clusters, false, lane);
+        if (item >= n_items) break;
         const ItemCoord c = decode_item(g, item);
         mbar_wait(&sh->a_full, a_ph);
         mbar_wait_cluster(&sh->peer_a_full, a_ph);
@@ -239,7 +314,10 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
       const uint32_t l_a_full = map_to_cta(&sh->peer_a_full, 0);
       int s = 0;
       uint32_t ph = 0, a_ph = 0;
-      for (int item = cluster_id; item < n_items; item += n_clusters) {
+      int it = 0;
+      for (;;) {
+        const int item = next_item(sh, g, it, cluster_id, n_clusters, false, lane);
+        if (item >= n_items) break;
         const ItemCoord c = decode_item(g, item);
         mbar_wait(&sh->a_full, a_ph);
         a_ph ^= 1;
@@ -270,7 +348,10 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
     const uint32_t l_pair_empty1 = map_to_cta(&sh->pair_tmem_empty[1], 0);
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int item = cluster_id; item < n_items; item += n_clusters) {
+    int it = 0;
+    for (;;) {
+      const int item = next_item(sh, g, it, cluster_id, n_clusters, false, lane);
+      if (item >= n_items) break;
       const ItemCoord c = decode_item(g, item);
       const long long a_row = ((g.a_rb0 ? g.a_rb0[c.problem] : 0) + g.a_rb_base + 2ll * c.rt + rank) *
                                   static_cast<long long>(kTileM) + row_in_tile;

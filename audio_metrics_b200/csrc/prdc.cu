@@ -372,12 +372,16 @@ static int engine_mode(int kb_count, long long row0) {
   return (two && (row0 / kTileM) % 2 == 0) ? 2 : 1;
 }
 
+// `counter`: a zeroed device int for the CTA-pair kernel's dynamic item hand-out
+// (AMB_SCHED=static keeps the round-robin assignment).
 template <class Epi>
 static int run_engine(int mode, cudaStream_t st, int dev, EngineGeom g, const Epi& epi, const char* what,
-                      double alg_pairs) {
+                      double alg_pairs, int* counter) {
   if (mode == 3) return launch_engine(st, dev, g, epi, what, alg_pairs);
   if (mode == 1) return launch_engine1(st, dev, g, epi, what, alg_pairs);
   g.n_rt = (g.n_rt + 1) / 2;   // row-tile pairs
+  const char* e = getenv("AMB_SCHED");
+  g.work_counter = (e && e[0] == 's') ? nullptr : counter;
   return launch_engine2(st, dev, g, epi, what, alg_pairs);
 }
 
@@ -385,7 +389,7 @@ template <int K>
 static int run_topk(cudaStream_t st, int dev, EngineGeom& g, const PackedPtrs& p, const KnnWs& w,
                     long long list_rows, long long a_row_base, double alg_pairs, int mode) {
   TopkEpi<K> epi{p.inv_scale, p.inv_scale, p.norm, w.keys, w.cols, list_rows, a_row_base};
-  return run_engine(mode, st, dev, g, epi, "pair_engine<topk>", alg_pairs);
+  return run_engine(mode, st, dev, g, epi, "pair_engine<topk>", alg_pairs, w.n_unresolved + 16);   // zeroed with n_unresolved
 }
 
 }  // namespace amb
@@ -565,7 +569,8 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   g.sbo_bytes = 512;
   CountEpi epi{pr.inv_scale, pr.norm, a_lo, a_hi, pc.inv_scale, pc.norm, b_lo, b_hi, col_count, row_recall,
                row_cover, row0, row0 + nrows, list, list_count, static_cast<unsigned long long>(cap)};
-  if ((rc = run_engine(mode, st, dev, g, epi, "pair_engine<count>", static_cast<double>(nrows) * m))) return rc;
+  if ((rc = run_engine(mode, st, dev, g, epi, "pair_engine<count>", static_cast<double>(nrows) * m,
+                       reinterpret_cast<int*>(q + 192)))) return rc;   // inside the zeroed 512-byte header
 
   const int blocks = 8 * sm_count(dev);
   if (dtype == AMB_F32)
