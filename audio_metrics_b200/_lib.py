@@ -24,6 +24,7 @@ SIGNATURES = {
     "amb_version": (_i, []),
     "amb_last_error": (C.c_char_p, []),
     "amb_launch_count": (_ll, []),
+    "amb_set_option": (_i, [C.c_char_p, _i]),
     "amb_profile_enable": (_i, [_i]),
     "amb_profile_read": (_i, [_vp]),
     "amb_cov_ws_bytes": (_sz, [_ll, _i]),

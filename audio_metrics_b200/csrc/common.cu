@@ -70,6 +70,11 @@ int sm_count(int dev) {
   return n;
 }
 
+static std::atomic<int> g_opt_jacobi_block{0}, g_opt_fad_ctas{0}, g_opt_reserve{0};
+int option_jacobi_block() { return g_opt_jacobi_block.load(std::memory_order_relaxed); }
+int option_fad_ctas() { return g_opt_fad_ctas.load(std::memory_order_relaxed); }
+int option_engine_reserve_sms() { return g_opt_reserve.load(std::memory_order_relaxed); }
+
 struct ProfRec { cudaEvent_t e0, e1; double pairs, flops; };
 static std::mutex g_prof_mu;
 static std::atomic<int> g_prof_on{0};
@@ -133,6 +138,26 @@ extern "C" {
 int amb_version(void) { return 100; }
 const char* amb_last_error(void) { return g_err; }
 long long amb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int amb_set_option(const char* name, int value) {
+  if (name && strcmp(name, "jacobi_block") == 0) {
+    if (value != 0 && value != 4 && value != 8 && value != 16)
+      return set_error(AMB_ERR_ARG, "amb_set_option: jacobi_block must be 0, 4, 8 or 16");
+    g_opt_jacobi_block.store(value);
+    return AMB_OK;
+  }
+  if (name && strcmp(name, "fad_ctas") == 0) {
+    if (value < 0) return set_error(AMB_ERR_ARG, "amb_set_option: fad_ctas must be >= 0");
+    g_opt_fad_ctas.store(value);
+    return AMB_OK;
+  }
+  if (name && strcmp(name, "engine_reserve_sms") == 0) {
+    if (value < 0 || value > 128) return set_error(AMB_ERR_ARG, "amb_set_option: engine_reserve_sms must be in [0, 128]");
+    g_opt_reserve.store(value);
+    return AMB_OK;
+  }
+  return set_error(AMB_ERR_ARG, "amb_set_option: unknown option '%s'", name ? name : "(null)");
+}
 
 int amb_profile_enable(int on) {
   g_prof_on.store(on ? 1 : 0);

@@ -92,7 +92,8 @@ int launch_engine2(cudaStream_t stream, int dev, EngineGeom g, const Epi& epi, c
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(pair_engine2)");
   const long long items = static_cast<long long>(g.n_problems) * g.n_rt * g.n_split;
   if (items <= 0) return AMB_OK;
-  int pairs = sm_count(dev) / 2;
+  int pairs = (sm_count(dev) - option_engine_reserve_sms()) / 2;   // SMs left to another stream's kernels
+  if (pairs < 1) pairs = 1;
   if (const char* e = getenv("AMB_GRID")) {
     const int v = atoi(e) / 2;
     if (v >= 1 && v < pairs) pairs = v;

@@ -476,6 +476,7 @@ static int launch_jacobi_block(cudaStream_t st, int dev, double* Gt, int d, int 
   long long want = static_cast<long long>(nb / 2) * n_mat;
   const long long cap = static_cast<long long>(per_sm) * sm_count(dev);
   if (want > cap) want = cap;
+  if (option_fad_ctas() > 0 && want > option_fad_ctas()) want = option_fad_ctas();   // CTAs loop over the block pairs
   void* args[] = {&Gt, &d, &n_mat, &tol, &stop_rot, &rot, &sweeps};
   rc = check_cuda(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fn), dim3(static_cast<unsigned>(want)),
                                               dim3(32 * BS), args, smem, st),
@@ -506,6 +507,11 @@ static int launch_jacobi(cudaStream_t st, int dev, double* Gt, int d, int n_mat,
     int bs = 16;
     const int sms = sm_count(dev);
     while (bs > 8 && static_cast<long long>(n_mat) * ((d + 2 * bs - 1) / (2 * bs)) * 2 <= sms) bs >>= 1;
+    if (option_fad_ctas() > 0) {   // stay within the CTA budget: larger blocks = fewer CTAs
+      bs = 16;
+      while (bs > 4 && static_cast<long long>(n_mat) * ((d + bs - 1) / bs) <= option_fad_ctas()) bs >>= 1;
+    }
+    if (option_jacobi_block()) bs = option_jacobi_block();
     if (const char* e = getenv("AMB_JACOBI_BS")) {
       const int v = atoi(e);
       if (v == 4 || v == 8 || v == 16) bs = v;
@@ -594,6 +600,7 @@ int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu
       int n_mat = 2 * batch - m0 < sms ? 2 * batch - m0 : sms;
       int C = sms / n_mat;
       if (C > 16) C = 16;
+      if (option_fad_ctas() > 0 && C * n_mat > option_fad_ctas()) C = option_fad_ctas() / n_mat > 0 ? option_fad_ctas() / n_mat : 1;
       double* Ap = G + static_cast<size_t>(m0) * mat;
       double* Lp = Lt + static_cast<size_t>(m0) * mat;
       int* pn = panel_n + m0;

@@ -26,6 +26,9 @@ struct DeviceGuard {
 };
 
 int sm_count(int dev);
+int option_jacobi_block();        // amb_set_option("jacobi_block")
+int option_fad_ctas();            // amb_set_option("fad_ctas")
+int option_engine_reserve_sms();  // amb_set_option("engine_reserve_sms")
 
 // Optional per-launch timing of the pair engine (amb_profile_*): CUDA events on the
 // launching stream around the kernel.  No-ops unless enabled.

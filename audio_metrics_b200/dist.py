@@ -49,6 +49,12 @@ def _allgather_rows(x: torch.Tensor, n: int, chunk: int, group):
     return out[:n]
 
 
+def _null():
+    import contextlib
+
+    return contextlib.nullcontext()
+
+
 def _allreduce(t: torch.Tensor, group):
     world, _ = _world(group)
     if world > 1:
@@ -64,6 +70,49 @@ class CudaOps:
 
         self._lib = _lib
         self.device = _lib.require_cuda(device)
+        self._side = None
+
+    # -- the N-independent FAD kernels (Cholesky, Jacobi: ~30 CTAs, latency-bound) run on a
+    #    high-priority side stream beside the PRDC sweeps, whose CTA pairs take their work
+    #    items dynamically and simply give up the SMs the side stream is holding
+    def side(self, *tensors):
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device, priority=-1)
+            main = torch.cuda.current_stream(self.device)
+            self._side.wait_stream(main)
+            for t in tensors:
+                t.record_stream(self._side)
+            L = self._lib.lib()
+            L.amb_set_option(b"fad_ctas", self.SHARED_SMS)     # the sweep beside it leaves these SMs alone
+            try:
+                with torch.cuda.stream(self._side):
+                    yield
+            finally:
+                L.amb_set_option(b"fad_ctas", 0)
+        return ctx()
+
+    SHARED_SMS = 16
+
+    def reserve_sms(self, on):
+        """The next all-pairs sweeps leave SHARED_SMS SMs to the side stream (on) / use them all (off)."""
+        self._lib.lib().amb_set_option(b"engine_reserve_sms", self.SHARED_SMS if on and self.use_side() else 0)
+
+    def use_side(self):
+        import os
+
+        return os.environ.get("AMB_FAD_SIDE", "1") != "0"
+
+    def join(self, *tensors):
+        if self._side is not None:
+            main = torch.cuda.current_stream(self.device)
+            main.wait_stream(self._side)
+            for t in tensors:
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(main)
 
     def moments(self, x):
         """fp64 [d + d*d] raw moments (column sums | Gram) of a row shard."""
@@ -190,14 +239,24 @@ def evaluate_sharded(ref_shard, cand_shard, n_ref, n_cand, metrics=("fad", "kd",
         mom = torch.cat([mom_ref, ops.moments(cand_shard)])
         _allreduce(mom, group)                       # one message: 2 (d + d^2) doubles
         half = d + d * d
-        s_ref = ops.stats_from_moments(mom[:half], n_ref, d)
-        s_cand = ops.stats_from_moments(mom[half:], n_cand, d)
-        pending["fad"] = ops.frechet(s_cand, s_ref)  # (cand, ref) as audio_metrics.py:257
+        with ops.side(mom) if hasattr(ops, "side") and ops.use_side() else _null():
+            s_ref = ops.stats_from_moments(mom[:half], n_ref, d)
+            s_cand = ops.stats_from_moments(mom[half:], n_cand, d)
+            pending["fad"] = ops.frechet(s_cand, s_ref)  # (cand, ref) as audio_metrics.py:257
     if want_kd or want_prdc:
         cand = _allgather_rows(cand_shard, n_cand, c_chunk, group)
     if want_prdc:
         ccand = ops.container(cand)
-        r_cand = _allgather_rows(ops.radii_rows(ccand, c_row0, c_nrows, k), n_cand, c_chunk, group).contiguous()
+        shared = want_fad and hasattr(ops, "reserve_sms")
+        if shared:
+            ccand.packed()                # (the pack kernels are not part of the sweep that shares the GPU)
+            ops.reserve_sms(True)         # the FAD kernels are running on the side stream now
+        try:
+            rr = ops.radii_rows(ccand, c_row0, c_nrows, k)
+        finally:
+            if shared:
+                ops.reserve_sms(False)
+        r_cand = _allgather_rows(rr, n_cand, c_chunk, group).contiguous()
         col, t = ops.count_rows(cref, ccand, r_ref, r_cand, r_row0, r_nrows, k)
         _allreduce(col, group)                       # [m] int32
         _allreduce(t, group)                         # 3 int64
@@ -222,6 +281,8 @@ def evaluate_sharded(ref_shard, cand_shard, n_ref, n_cand, metrics=("fad", "kd",
             pending["kd"] = local
 
     # ---- the one read-back
+    if want_fad and hasattr(ops, "join"):
+        ops.join(pending["fad"])
     result = {}
     if want_fad:
         result["fad"] = float(pending["fad"])

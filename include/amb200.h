@@ -56,6 +56,16 @@ long long amb_launch_count(void);
 int amb_profile_enable(int on);
 int amb_profile_read(double* out);
 
+/* Process-wide tuning options (names are stable, unknown names return AMB_ERR_ARG):
+ *   "jacobi_block"        0 = automatic, 4 / 8 / 16 = columns per block of the Frechet distance's
+ *                         block-Jacobi kernel.
+ *   "fad_ctas"            0 = automatic, else the most CTAs the Frechet distance's cooperative
+ *                         kernels (Cholesky, Jacobi) may use.
+ *   "engine_reserve_sms"  SMs the all-pairs sweeps (amb_knn_radii, amb_prdc_counts) leave free.
+ * The last two let the N-independent Frechet kernels run on a second stream beside a sweep:
+ * the sweep keeps clear of as many SMs as the Frechet kernels are limited to. */
+int amb_set_option(const char* name, int value);
+
 /* ------------------------------------------------------------------ statistics
  * AudioMetricsData.add / recompute_stats (data.py:37-58): batch mean and unbiased
  * covariance, kept here as fp64 raw moments so that batches, GPUs and calls add. */
