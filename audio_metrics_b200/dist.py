@@ -239,7 +239,8 @@ def evaluate_sharded(ref_shard, cand_shard, n_ref, n_cand, metrics=("fad", "kd",
         mom = torch.cat([mom_ref, ops.moments(cand_shard)])
         _allreduce(mom, group)                       # one message: 2 (d + d^2) doubles
         half = d + d * d
-        with ops.side(mom) if hasattr(ops, "side") and ops.use_side() else _null():
+        overlap = want_prdc and hasattr(ops, "side") and ops.use_side()   # alone, FAD runs at full width
+        with ops.side(mom) if overlap else _null():
             s_ref = ops.stats_from_moments(mom[:half], n_ref, d)
             s_cand = ops.stats_from_moments(mom[half:], n_cand, d)
             pending["fad"] = ops.frechet(s_cand, s_ref)  # (cand, ref) as audio_metrics.py:257
@@ -247,7 +248,7 @@ def evaluate_sharded(ref_shard, cand_shard, n_ref, n_cand, metrics=("fad", "kd",
         cand = _allgather_rows(cand_shard, n_cand, c_chunk, group)
     if want_prdc:
         ccand = ops.container(cand)
-        shared = want_fad and hasattr(ops, "reserve_sms")
+        shared = want_fad and hasattr(ops, "reserve_sms") and ops.use_side()
         if shared:
             ccand.packed()                # (the pack kernels are not part of the sweep that shares the GPU)
             ops.reserve_sms(True)         # the FAD kernels are running on the side stream now
