@@ -37,14 +37,16 @@ def _stats64(x):
 def test_single_pass_and_split_sweeps_agree(cuda_device, monkeypatch, n, m, d, k):
     ref, cand = make_sets_numpy(n, m, d, seed=n + d + k)
     out = {}
-    for name, passes, cta2 in (("pair", "1", "1"), ("single", "1", "0"), ("split", "3", "0")):
+    for name, passes, cta2, sched in (("pair", "1", "1", "dynamic"), ("pair_static", "1", "1", "static"),
+                                      ("single", "1", "0", "dynamic"), ("split", "3", "0", "dynamic")):
         monkeypatch.setenv("AMB_PASSES", passes)
         monkeypatch.setenv("AMB_CTA2", cta2)
+        monkeypatch.setenv("AMB_SCHED", sched)
         R, C = _amd(ref), _amd(cand)
         r_ref = nearest_neighbour_distances(R, k)
         col, rec, cov, tot = prdc_totals(R, C, k)
         out[name] = (r_ref.cpu().numpy(), col.cpu().numpy(), rec.cpu().numpy(), cov.cpu().numpy(), int(tot[4]))
-    for other in ("single", "split"):
+    for other in ("pair_static", "single", "split"):
         for a, b in zip(out["pair"][:4], out[other][:4]):
             assert np.array_equal(a, b)
     # the single-pass band is wider: more pairs go through the exact refine
@@ -145,6 +147,32 @@ def test_frechet_factor_paths_agree(cuda_device, monkeypatch):
     for bs in ("16", "8", "4"):                      # Jacobi block sizes
         monkeypatch.setenv("AMB_JACOBI_BS", bs)
         assert frechet_distance(A, B) == pytest.approx(chol, rel=1e-10)
+
+
+def test_options_and_shared_gpu_step(cuda_device):
+    """amb_set_option, and the overlapped step (FAD on a side stream beside a narrowed sweep) against
+    the plain sequential calls."""
+    from audio_metrics_b200 import _lib, kernel_distance
+    from audio_metrics_b200.dist import evaluate_sharded
+    L = _lib.lib()
+    assert L.amb_set_option(b"no_such_option", 1) == _lib.AMB_ERR_ARG
+    assert L.amb_set_option(b"jacobi_block", 5) == _lib.AMB_ERR_ARG
+    for name in (b"jacobi_block", b"fad_ctas", b"engine_reserve_sms"):
+        assert L.amb_set_option(name, 16) == 0 and L.amb_set_option(name, 0) == 0
+    ref, cand = make_sets_numpy(6000, 5200, 512, seed=17)
+    R, C = _amd(ref), _amd(cand)
+    want = dict(fad=frechet_distance(C, R), **kernel_distance(C, R), **prdc(R, C, 5))
+    got = evaluate_sharded(torch.from_numpy(ref).cuda(), torch.from_numpy(cand).cuda(), 6000, 5200, nearest_k=5)
+    assert got["fad"] == pytest.approx(want["fad"], rel=1e-9)
+    for key in ("kernel_distance_mean", "kernel_distance_std"):      # host numpy vs device reduction of the same 100 values
+        assert got[key] == pytest.approx(want[key], rel=1e-12), key
+    for key in ("precision", "recall", "density", "coverage"):
+        assert got[key] == want[key], key
+    L.amb_set_option(b"engine_reserve_sms", 100)       # a very narrow sweep gives the same counts
+    try:
+        assert prdc(_amd(ref), _amd(cand), 5) == {k: want[k] for k in ("precision", "recall", "density", "coverage")}
+    finally:
+        L.amb_set_option(b"engine_reserve_sms", 0)
 
 
 # ------------------------------------------------------- full-size properties (BASELINE N)
