@@ -100,15 +100,24 @@ knn_refine_kernel(const T* __restrict__ X, long long ld, int d, long long n, lon
     last_col = best_col;
     if (lane == r) { sel_key = best; sel_col = best_col; }
   }
-  // --- exact squared distances of the selected candidates (lane c <- candidate c)
+  // --- exact squared distances of the selected candidates (lane c <- candidate c).  Only
+  // candidates that can be among the k+1 nearest are evaluated: with s_k the (k+1)-th smallest
+  // approximate key, k+1 candidates have exact key <= s_k + band, so a candidate whose
+  // approximate key exceeds s_k + 2 band (exact key > s_k + band) cannot be one of them.
+  const float nx_f = norm[i];
+  const float band_f = filter_band(single_pass, nx_f, rho[i], max_norm);
+  const float s_k = __shfl_sync(0xffffffffu, sel_key, k);      // +inf when fewer than k+1 candidates exist
+  const float cut = s_k + 2.0f * band_f + 1e-6f * (fabsf(s_k) + nx_f);
   double my_d2 = __longlong_as_double(0x7ff0000000000000ll);
   int n_sel = 0;
   for (int c = 0; c < Kt; ++c) {
     const int col = __shfl_sync(0xffffffffu, sel_col, c);
     if (col < 0) break;
+    const float key_c = __shfl_sync(0xffffffffu, sel_key, c);
+    n_sel = c + 1;
+    if (key_c > cut) continue;                                  // stays +inf: never among the k+1 smallest
     const double d2 = exact_sqdist_warp(xi, X + static_cast<long long>(col) * ld, d, lane);
     if (lane == c) my_d2 = d2;
-    n_sel = c + 1;
   }
   // --- (k+1)-th smallest exact value among them: rank by (value, lane)
   int rank = 0;
@@ -126,8 +135,8 @@ knn_refine_kernel(const T* __restrict__ X, long long ld, int d, long long n, lon
   const float t_last = __shfl_sync(0xffffffffu, sel_key, Kt - 1);
   const int last_sel = __shfl_sync(0xffffffffu, sel_col, Kt - 1);
   if (ok && last_sel >= 0) {
-    const float nx = norm[i];
-    const float band = filter_band(single_pass, nx, rho[i], max_norm);
+    const float nx = nx_f;
+    const float band = band_f;
     const double bound = static_cast<double>(nx) + static_cast<double>(t_last) - static_cast<double>(band);
     if (!(r2 < bound)) ok = false;
   }

@@ -20,6 +20,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+_SIDE_STREAMS = {}
 ROW_ALIGN = 256     # two row tiles: shards start on an even tile, so the CTA-pair engine applies
 
 
@@ -81,21 +82,34 @@ class CudaOps:
         @contextlib.contextmanager
         def ctx():
             if self._side is None:
-                self._side = torch.cuda.Stream(self.device, priority=-1)
+                # ONE side stream per device for the life of the process: torch hands out pooled
+                # streams round-robin, and a fresh one per call eventually lands on the hardware queue
+                # of the main stream, which serialises the two (seen as 100-200 ms outlier steps)
+                key = self.device.index
+                if key not in _SIDE_STREAMS:
+                    _SIDE_STREAMS[key] = torch.cuda.Stream(self.device, priority=-1)
+                self._side = _SIDE_STREAMS[key]
             main = torch.cuda.current_stream(self.device)
             self._side.wait_stream(main)
-            for t in tensors:
-                t.record_stream(self._side)
+            # (no record_stream: the caller keeps `tensors` alive until join(), and marking them would
+            #  make the caching allocator hold their blocks back across streams)
             L = self._lib.lib()
             L.amb_set_option(b"fad_ctas", self.SHARED_SMS)     # the sweep beside it leaves these SMs alone
             try:
                 with torch.cuda.stream(self._side):
+                    if self.trace is not None:
+                        e0 = torch.cuda.Event(enable_timing=True); e0.record()
                     yield
+                    if self.trace is not None:
+                        e1 = torch.cuda.Event(enable_timing=True); e1.record()
+                        self.trace.append((e0, e1))
             finally:
                 L.amb_set_option(b"fad_ctas", 0)
         return ctx()
 
-    SHARED_SMS = 16
+    import os as _os
+    SHARED_SMS = int(_os.environ.get("AMB_SHARED_SMS", "16"))
+    trace = None     # set to a list to collect (start, end) CUDA events of the side-stream section
 
     def reserve_sms(self, on):
         """The next all-pairs sweeps leave SHARED_SMS SMs to the side stream (on) / use them all (off)."""
@@ -110,9 +124,6 @@ class CudaOps:
         if self._side is not None:
             main = torch.cuda.current_stream(self.device)
             main.wait_stream(self._side)
-            for t in tensors:
-                if isinstance(t, torch.Tensor):
-                    t.record_stream(main)
 
     def moments(self, x):
         """fp64 [d + d*d] raw moments (column sums | Gram) of a row shard."""
@@ -248,10 +259,12 @@ def evaluate_sharded(ref_shard, cand_shard, n_ref, n_cand, metrics=("fad", "kd",
         cand = _allgather_rows(cand_shard, n_cand, c_chunk, group)
     if want_prdc:
         ccand = ops.container(cand)
+        # While the FAD kernels run on the side stream (about 20 ms) the candidate radii sweep
+        # (about 35 ms) keeps clear of their SMs; the count sweep afterwards is full width again.
         shared = want_fad and hasattr(ops, "reserve_sms") and ops.use_side()
         if shared:
             ccand.packed()                # (the pack kernels are not part of the sweep that shares the GPU)
-            ops.reserve_sms(True)         # the FAD kernels are running on the side stream now
+            ops.reserve_sms(True)
         try:
             rr = ops.radii_rows(ccand, c_row0, c_nrows, k)
         finally:
