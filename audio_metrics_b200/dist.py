@@ -113,7 +113,7 @@ class CudaOps:
 
     def reserve_sms(self, on):
         """The next all-pairs sweeps leave SHARED_SMS SMs to the side stream (on) / use them all (off)."""
-        self._lib.lib().amb_set_option(b"engine_reserve_sms", self.SHARED_SMS if on and self.use_side() else 0)
+        self._lib.lib().amb_set_option(b"engine_reserve_sms", self.SHARED_SMS if on else 0)
 
     def use_side(self):
         import os
@@ -234,48 +234,64 @@ def evaluate_sharded(ref_shard, cand_shard, n_ref, n_cand, metrics=("fad", "kd",
     ev_ref, ev_cand = ready if ready is not None else (None, None)
     pending = {}                                     # device-side results, read back at the end
 
-    # ---- reference-only work
-    wait(ev_ref)
-    if want_fad:
-        mom_ref = ops.moments(ref_shard)
-    if want_kd or want_prdc:
-        ref = _allgather_rows(ref_shard, n_ref, r_chunk, group)
-    if want_prdc:
-        cref = ops.container(ref)
-        r_ref = _allgather_rows(ops.radii_rows(cref, r_row0, r_nrows, k), n_ref, r_chunk, group).contiguous()
+    overlap = want_fad and want_prdc and hasattr(ops, "side") and ops.use_side()   # alone, FAD runs at full width
+    # One GPU: reference-only work first, so that a candidate shard still in flight (ready=) is touched
+    # late; the FAD kernels then run beside the candidate radii sweep.  Several GPUs: the sweeps are
+    # 1/world as long while FAD is N-independent, so FAD is started first and all sweeps leave it room.
+    fad_first = overlap and world > 1
 
-    # ---- candidate
-    wait(ev_cand)
-    if want_fad:
-        mom = torch.cat([mom_ref, ops.moments(cand_shard)])
+    def fad(mom_ref, mom_cand):
+        mom = torch.cat([mom_ref, mom_cand])
         _allreduce(mom, group)                       # one message: 2 (d + d^2) doubles
         half = d + d * d
-        overlap = want_prdc and hasattr(ops, "side") and ops.use_side()   # alone, FAD runs at full width
         with ops.side(mom) if overlap else _null():
             s_ref = ops.stats_from_moments(mom[:half], n_ref, d)
             s_cand = ops.stats_from_moments(mom[half:], n_cand, d)
             pending["fad"] = ops.frechet(s_cand, s_ref)  # (cand, ref) as audio_metrics.py:257
+        pending["_mom"] = mom                        # alive until the read-back (used on the side stream)
+
+    def narrowed(on):
+        if overlap:
+            ops.reserve_sms(on)
+
+    # ---- reference-only work
+    wait(ev_ref)
+    if want_fad:
+        mom_ref = ops.moments(ref_shard)
+    if fad_first:
+        wait(ev_cand)
+        fad(mom_ref, ops.moments(cand_shard))
     if want_kd or want_prdc:
-        cand = _allgather_rows(cand_shard, n_cand, c_chunk, group)
-    if want_prdc:
-        ccand = ops.container(cand)
-        # While the FAD kernels run on the side stream (about 20 ms) the candidate radii sweep
-        # (about 35 ms) keeps clear of their SMs; the count sweep afterwards is full width again.
-        shared = want_fad and hasattr(ops, "reserve_sms") and ops.use_side()
-        if shared:
-            ccand.packed()                # (the pack kernels are not part of the sweep that shares the GPU)
-            ops.reserve_sms(True)
-        try:
-            rr = ops.radii_rows(ccand, c_row0, c_nrows, k)
-        finally:
-            if shared:
-                ops.reserve_sms(False)
-        r_cand = _allgather_rows(rr, n_cand, c_chunk, group).contiguous()
-        col, t = ops.count_rows(cref, ccand, r_ref, r_cand, r_row0, r_nrows, k)
-        _allreduce(col, group)                       # [m] int32
-        _allreduce(t, group)                         # 3 int64
-        pending["prdc"] = torch.cat([torch.stack([(col > 0).sum(dtype=torch.int64), col.sum(dtype=torch.int64)]),
-                                     t.to(torch.int64)])
+        ref = _allgather_rows(ref_shard, n_ref, r_chunk, group)
+    try:
+        if want_prdc:
+            cref = ops.container(ref)
+            if fad_first:
+                cref.packed()
+                narrowed(True)
+            r_ref = _allgather_rows(ops.radii_rows(cref, r_row0, r_nrows, k), n_ref, r_chunk, group).contiguous()
+
+        # ---- candidate
+        wait(ev_cand)
+        if want_fad and not fad_first:
+            fad(mom_ref, ops.moments(cand_shard))
+        if want_kd or want_prdc:
+            cand = _allgather_rows(cand_shard, n_cand, c_chunk, group)
+        if want_prdc:
+            ccand = ops.container(cand)
+            if overlap and not fad_first:
+                ccand.packed()            # (the pack kernels are not part of the sweep that shares the GPU)
+                narrowed(True)            # FAD (about 20 ms) runs beside the candidate radii sweep (about 35 ms)
+            r_cand = _allgather_rows(ops.radii_rows(ccand, c_row0, c_nrows, k), n_cand, c_chunk, group).contiguous()
+            if not fad_first:
+                narrowed(False)           # ... and the count sweep is full width again
+            col, t = ops.count_rows(cref, ccand, r_ref, r_cand, r_row0, r_nrows, k)
+            _allreduce(col, group)                       # [m] int32
+            _allreduce(t, group)                         # 3 int64
+            pending["prdc"] = torch.cat([torch.stack([(col > 0).sum(dtype=torch.int64), col.sum(dtype=torch.int64)]),
+                                         t.to(torch.int64)])
+    finally:
+        narrowed(False)
 
     if want_kd:
         n_s = min(n_ref, n_cand)
