@@ -97,7 +97,8 @@ int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu
 
 /* --------------------------------------------------------------- packed operands
  * Embeddings are rewritten once per set into the tensor-core operand format
- * (two fp16 planes + per-row scale and squared norm); KD and PRDC consume that. */
+ * (two fp16 planes with one power-of-two scale per 256-row tile, plus per-row
+ * squared norm and hi-plane residual); KD and PRDC consume that. */
 size_t amb_packed_bytes(long long n, int d);
 int amb_pack(int dev, amb_stream_t stream, const void* X, int dtype, long long n, int d,
              long long ld, void* packed);
@@ -123,8 +124,8 @@ int amb_kd_subsets(int dev, amb_stream_t stream, const void* F1, long long n1, l
  * nearest_neighbour_distances (metrics/prdc.py:4-14): radius_i = (k+1)-th
  * smallest Euclidean distance from row i to all rows of the set (self
  * included), returned as the correctly rounded fp32 value of the exact distance.
- * Computes radii for rows [row0, row0+nrows) of the set (row0 % 128 == 0)
- * against all n rows.  radii: [nrows] fp32.  1 <= k <= 29 and k+1 <= n (the
+ * Computes radii for rows [row0, row0+nrows) of the set (row0 % 128 == 0; shards that
+ * start on an even tile, row0 % 256 == 0, run on the CTA-pair kernel) against all n rows.  radii: [nrows] fp32.  1 <= k <= 29 and k+1 <= n (the
  * reference's kthvalue raises for k+1 > n). */
 size_t amb_knn_ws_bytes(long long nrows, long long n, int d, int k);
 int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long long ld,
