@@ -345,6 +345,18 @@ static int pick_split(int dev, long long n_rt, long long n_ct, int kb_count, lon
   return best_s;
 }
 
+// The CTA-pair engine hands out work items dynamically, so the tail of a sweep is at most one
+// item long: the count sweep is cut into four column splits to shorten it (measured 29.7 -> 28.0 ms
+// at 200k x 200k).  The radii sweep is not: every split restarts its candidate lists, and the
+// extra insertions cost more than the tail (30.9 -> 32.1 ms with two splits).
+constexpr int kTailSplitTopk = 1;
+constexpr int kTailSplitCount = 4;
+static int tail_split(int mode, int n_split, int n_ct, int want) {
+  if (mode != 2 || n_split != 1 || n_ct < 64 * want) return n_split;
+  if (const char* e = getenv("AMB_TAIL_SPLIT")) return atoi(e) >= 1 && atoi(e) <= want ? atoi(e) : n_split;
+  return want;
+}
+
 struct KnnWs {
   float* keys;
   int* cols;
@@ -413,7 +425,7 @@ size_t amb_knn_ws_bytes(long long nrows, long long n, int d, int k) {
   // upper bound of pick_split() without knowing the device: one split once there
   // are clearly >= 2 row tiles per SM (up to 160 SMs), else the cap of 64
   const long long n_rt = (nrows + kTileM - 1) / kTileM;
-  const int bound = n_rt >= 2ll * 160 ? 1 : 64;
+  const int bound = n_rt >= 2ll * 160 ? kTailSplitTopk : 64;
   return knn_ws(nullptr, nrows, Kt, bound).bytes;
 }
 
@@ -442,6 +454,7 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
     const int v = atoi(e);
     if (v >= 1 && v <= 64 && v <= n_ct) n_split = v;
   }
+  n_split = tail_split(engine_mode(p.kb_count, row0), n_split, static_cast<int>(n_ct), kTailSplitTopk);
   KnnWs w = knn_ws(ws, nrows, Kt, n_split);
   if (!ws || ws_bytes < w.bytes) return set_error(AMB_ERR_WS, "amb_knn_radii: workspace %zu < %zu", ws_bytes, w.bytes);
   const long long list_rows = round_up_ll(nrows, 2 * kTileM);
@@ -570,6 +583,7 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   g.n_ct = static_cast<int>(pc.rows_pad / kTileN);
   // the single-pass kernel keeps the A panel in shared memory: no L2 pressure from A, one split
   g.n_split = pick_split(dev, g.n_rt, g.n_ct, pc.kb_count, sp ? 0 : kCountSplitBytes);
+  g.n_split = tail_split(mode, g.n_split, g.n_ct, kTailSplitCount);
   if (const char* e = getenv("AMB_COUNT_SPLIT")) {   // tuning knob
     const int v = atoi(e);
     if (v >= 1 && v <= 64 && v <= g.n_ct) g.n_split = v;

@@ -41,7 +41,7 @@ def test_size_queries_need_no_gpu():
     assert L.amb_cov_ws_bytes(100000, 512) > 0
     assert L.amb_frechet_ws_bytes(3, 512) >= 3 * 3 * 512 * 512 * 8
     assert L.amb_kd_ws_bytes(100, 1000, 512) > 2 * 100 * 1024 * 512 * 4
-    assert L.amb_knn_ws_bytes(200000, 200000, 512, 5) < 64 << 20      # one split at bench size
+    assert L.amb_knn_ws_bytes(200000, 200000, 512, 5) < 64 << 20      # one column split at bench size
     assert L.amb_knn_ws_bytes(1000, 1000, 512, 40) == 0               # unsupported k
     assert L.amb_prdc_list_cap(200000, 200000) == 16 * 400000
     assert L.amb_prdc_ws_bytes(1000, 1000) > L.amb_prdc_list_cap(1000, 1000) * 8
