@@ -191,29 +191,31 @@ struct TopkEpi {
     // branch-free scan first: most chunks hold nothing below the row's current
     // K-th smallest key
     float t[32];
-    float m0 = kInf, m1 = kInf, m2 = kInf, m3 = kInf;
+    float g[4];                              // minimum of each 8-column group
     const float sc = cv[0][c0] * r.m2isr;   // -2 / (scale_a scale_b): one per tile (powers of two, exact)
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      t[j + 0] = fmaf(f32(acc[j + 0]), sc, cv[1][c0 + j + 0]);
-      t[j + 1] = fmaf(f32(acc[j + 1]), sc, cv[1][c0 + j + 1]);
-      t[j + 2] = fmaf(f32(acc[j + 2]), sc, cv[1][c0 + j + 2]);
-      t[j + 3] = fmaf(f32(acc[j + 3]), sc, cv[1][c0 + j + 3]);
-      m0 = fminf(m0, t[j + 0]);
-      m1 = fminf(m1, t[j + 1]);
-      m2 = fminf(m2, t[j + 2]);
-      m3 = fminf(m3, t[j + 3]);
+    for (int h = 0; h < 4; ++h) {
+      float ma = kInf, mb = kInf;
+#pragma unroll
+      for (int j = 8 * h; j < 8 * h + 8; j += 2) {
+        t[j + 0] = fmaf(f32(acc[j + 0]), sc, cv[1][c0 + j + 0]);
+        t[j + 1] = fmaf(f32(acc[j + 1]), sc, cv[1][c0 + j + 1]);
+        ma = fminf(ma, t[j + 0]);
+        mb = fminf(mb, t[j + 1]);
+      }
+      g[h] = fminf(ma, mb);
     }
-    const float tmin = fminf(fminf(m0, m1), fminf(m2, m3));
+    const float tmin = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
     const float thr = fminf(r.v[K - 1], *r.peer);
     if (__any_sync(0xffffffffu, tmin < thr)) {
-      // some row of the warp takes new candidates.  Per 8-column group of the chunk:
-      // each thread builds the bit mask of its qualifying columns, parks the 8 keys in
-      // its private shared-memory slots, and the warp loops while any lane still has a
-      // bit to consume (usually one trip): a lane picks its lowest set column, reloads
+      // some row of the warp takes new candidates.  Per 8-column group of the chunk that
+      // holds one: each thread builds the bit mask of its qualifying columns, parks the 8
+      // keys in its private shared-memory slots, and the warp loops while any lane still
+      // has a bit to consume (usually one trip): a lane picks its lowest set column, reloads
       // that key by dynamic index and inserts it; the threshold tightens as it goes.
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
+        if (!__any_sync(0xffffffffu, g[h] < thr)) continue;
         unsigned mask = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
