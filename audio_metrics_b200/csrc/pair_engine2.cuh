@@ -16,7 +16,10 @@
 //   empty[s]           local   L's MMA commit, multicast to both CTAs: slot s may be refilled
 //   a_full/peer_a_full, a_empty   the same three for the resident A panel
 //   tmem_full[acc]     local   L's MMA commit, multicast: accumulator acc is complete
-//   tmem_empty[acc]    local   this CTA's 8 epilogue warps drained acc (gates the column-vector copies)
+//   cv_full/cv_empty[q] local  the per-tile column vectors live in their own four-slot ring, so the
+//                              producer never waits for the epilogue before prefetching the next
+//                              tile's B slots (with the vectors in the accumulator's double buffer
+//                              it did, and every tile started on a cold ring)
 //   pair_tmem_empty[acc] in L  all 16 epilogue warps of the pair drained acc (gates L's next MMAs)
 //
 // Work items are handed out DYNAMICALLY (g.work_counter != nullptr): the leader's producer warp
@@ -31,19 +34,20 @@
 namespace amb {
 
 constexpr int kStage2Bytes = 2 * kChunkBytes;            // this CTA's B half, two k blocks (K = 64)
+constexpr int kCvSlots = 4;
 constexpr int kSchedSlots = 2;
 constexpr int kSchedConsumers = 2 * (kEngineThreads / 32) - 1;   // every warp of the pair but the scheduler
 
 template <int NCV>
 struct EngineSmem2T {
-  alignas(128) float colvec[2][NCV][kTileN];
+  alignas(128) float colvec[kCvSlots][NCV][kTileN];
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t peer_full[kMaxStages];
   uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
   uint64_t pair_tmem_empty[2];
-  uint64_t cv_full[2];
+  uint64_t cv_full[kCvSlots];
+  uint64_t cv_empty[kCvSlots];
   uint64_t a_full;
   uint64_t peer_a_full;
   uint64_t a_empty;
@@ -193,9 +197,11 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sh->tmem_full[a], 1);
-      mbar_init(&sh->tmem_empty[a], kEpiWarps);
       mbar_init(&sh->pair_tmem_empty[a], 2 * kEpiWarps);
-      mbar_init(&sh->cv_full[a], 1);
+    }
+    for (int q = 0; q < kCvSlots; ++q) {
+      mbar_init(&sh->cv_full[q], 1);
+      mbar_init(&sh->cv_empty[q], kEpiWarps);
     }
     mbar_init(&sh->a_full, 1);
     mbar_init(&sh->peer_a_full, 1);
@@ -219,8 +225,7 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
     // ------------------------------------------------------------ producer (both CTAs)
     int s = 0;
     uint32_t ph = 0, a_ph = 0;
-    int acc = 0;
-    uint32_t acc_ph = 0;
+    uint32_t tile = 0;         // running column-tile count: column-vector slot tile % kCvSlots
     int it = 0;
     for (;;) {
       const int item = next_item(sh, g, it, cluster_id, n_clusters, leader, lane);
@@ -240,16 +245,16 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
       for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
         // this CTA's half of the B tile: row block 2 ct + rank, all k blocks contiguous
         const __half* b_src = g.b_planes + (b_rb_base + 2ll * ct + rank) * kb_count * kChunkHalfs;
-        mbar_wait(&sh->tmem_empty[acc], acc_ph ^ 1);
+        const int q = tile & (kCvSlots - 1);
+        mbar_wait(&sh->cv_empty[q], ((tile / kCvSlots) & 1u) ^ 1u);   // the epilogue of four tiles ago
         if (elect_one()) {
-          mbar_expect_tx(&sh->cv_full[acc], Epi::kColVecs * kTileN * 4);
+          mbar_expect_tx(&sh->cv_full[q], Epi::kColVecs * kTileN * 4);
 #pragma unroll
           for (int v = 0; v < Epi::kColVecs; ++v)
-            bulk_g2s(sh->colvec[acc][v], epi.colvec_ptr(v) + (b_rb_base + 2ll * ct) * kBlockRows, kTileN * 4,
-                     &sh->cv_full[acc]);
+            bulk_g2s(sh->colvec[q][v], epi.colvec_ptr(v) + (b_rb_base + 2ll * ct) * kBlockRows, kTileN * 4,
+                     &sh->cv_full[q]);
         }
-        acc ^= 1;
-        if (acc == 0) acc_ph ^= 1;
+        ++tile;
         for (int j = 0; j < n_kp; ++j) {
           mbar_wait(&sh->empty[s], ph ^ 1);
           if (elect_one()) {
@@ -348,6 +353,7 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
     const uint32_t l_pair_empty1 = map_to_cta(&sh->pair_tmem_empty[1], 0);
     int acc = 0;
     uint32_t acc_ph = 0;
+    uint32_t tile = 0;
     int it = 0;
     for (;;) {
       const int item = next_item(sh, g, it, cluster_id, n_clusters, false, lane);
@@ -361,7 +367,8 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
       if (Epi::kScratch) named_bar_sync(1 + quarter, 64);
       for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
         const long long b_row0 = b_row_base + static_cast<long long>(ct) * kTileN;
-        mbar_wait(&sh->cv_full[acc], acc_ph);
+        const int q = tile & (kCvSlots - 1);
+        mbar_wait(&sh->cv_full[q], (tile / kCvSlots) & 1u);
         mbar_wait_cluster(&sh->tmem_full[acc], acc_ph);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc) * kTileN +
@@ -371,14 +378,15 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
           uint32_t r[32];
           tmem_ld32(t_addr + c0, r);
           tmem_wait_ld();
-          epi.chunk(row, r, sh->colvec[acc], c0, ct * kTileN + c0, b_row0 + c0, scratch);
+          epi.chunk(row, r, sh->colvec[q], c0, ct * kTileN + c0, b_row0 + c0, scratch);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&sh->tmem_empty[acc]);
+          mbar_arrive(&sh->cv_empty[q]);
           mbar_arrive_cluster(acc == 0 ? l_pair_empty0 : l_pair_empty1);
         }
+        ++tile;
         acc ^= 1;
         if (acc == 0) acc_ph ^= 1;
       }
