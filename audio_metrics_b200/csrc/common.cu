@@ -109,7 +109,8 @@ PackedLayout packed_layout(long long n_rows, int d) {
   L.off_norm = L.off_inv + static_cast<size_t>(L.rows_pad) * 4;
   L.off_rho = L.off_norm + static_cast<size_t>(L.rows_pad) * 4;
   L.off_exp = L.off_rho + static_cast<size_t>(L.rows_pad) * 4;
-  L.bytes = L.off_exp + static_cast<size_t>(L.rows_pad) * 4;
+  L.off_cmin = L.off_exp + static_cast<size_t>(L.rows_pad) * 4;
+  L.bytes = L.off_cmin + static_cast<size_t>(L.rows_pad / 32) * 4;
   L.bytes = static_cast<size_t>(round_up_ll(static_cast<long long>(L.bytes), 256));
   return L;
 }
@@ -124,6 +125,7 @@ PackedPtrs packed_ptrs(void* blob, long long n_rows, int d) {
   p.norm = reinterpret_cast<float*>(b + L.off_norm);
   p.rho = reinterpret_cast<float*>(b + L.off_rho);
   p.row_exp = reinterpret_cast<int*>(b + L.off_exp);
+  p.cmin = reinterpret_cast<float*>(b + L.off_cmin);
   p.rows_pad = L.rows_pad;
   p.kb_count = L.kb_count;
   return p;
@@ -201,7 +203,7 @@ int amb_pack(int dev, amb_stream_t stream, const void* X, int dtype, long long n
   if (!guard.ok) return AMB_ERR_CUDA;
   PackedPtrs p = packed_ptrs(packed, n, d);
   return launch_pack(static_cast<cudaStream_t>(stream), X, dtype, ld, d, n, nullptr, n, 0,
-                     p.rows_pad, p.planes, p.plane_halfs, p.kb_count, p.inv_scale, p.norm, p.rho, p.row_exp);
+                     p.rows_pad, p.planes, p.plane_halfs, p.kb_count, p.inv_scale, p.norm, p.rho, p.row_exp, p.cmin);
 }
 
 int amb_debug_dot_matrix(int dev, amb_stream_t stream, const void* packed_a, long long na,

@@ -24,13 +24,14 @@ struct DumpEpi {
   int checksum_only;       // 1: C[a_row] = sum_j dot (timing runs; no N x M write)
   struct Row { float isr; long long a_row; float sum; };
   __device__ const float* colvec_ptr(int) const { return inv_b; }
+  __device__ const float* cmin_ptr() const { return nullptr; }
   __device__ void row_begin(Row& r, const ItemCoord&, long long a_row, int, float*) const {
     r.isr = inv_a[a_row];
     r.a_row = a_row;
     r.sum = 0.f;
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
-                        long long b_row0, float*) const {
+                        long long b_row0, float*, float) const {
     if (r.a_row >= na) return;
     const float sc = cv[0][c0] * r.isr;
     if (checksum_only) {
@@ -68,6 +69,7 @@ struct KdEpi {
   double* partial;
   struct Row { double sum; double gr; float na; int row_in_problem; bool valid; bool sym; };
   __device__ const float* colvec_ptr(int) const { return inv_b; }
+  __device__ const float* cmin_ptr() const { return nullptr; }
   __device__ void row_begin(Row& r, const ItemCoord& c, long long a_row, int, float*) const {
     r.row_in_problem = c.rt * kTileM + static_cast<int>(a_row % kTileM);
     r.valid = r.row_in_problem < m_valid;
@@ -92,7 +94,7 @@ struct KdEpi {
     }
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0,
-                        int col0, long long b_row0, float*) const {
+                        int col0, long long b_row0, float*, float) const {
     if (!r.valid) return;
     const bool edge = (col0 + 32 > m_valid) || (r.sym && col0 <= r.row_in_problem && r.row_in_problem < col0 + 32);
     if (!edge && kernel_type == AMB_KERNEL_POLY && degree == 3) {
@@ -152,6 +154,17 @@ __host__ __device__ inline float band_key1(float nrm_x, float rho_x, float nrm_y
   return 2.0f * ((rho_x * ay + ax * rho_y_max) * 1.002f + kBandAcc1 * ax * ay) + kBandAbs * (nrm_x + nrm_y_max);
 }
 
+// Bound on the raw accumulator for "some column of this chunk has key  |y_j|^2 + sc acc_j < thr":
+// with |y_j|^2 >= cmin for the whole chunk and sc < 0 that needs  acc_j > (thr - cmin) / sc.  sc is a
+// power of two, so the quotient is exact; the bound is loosened by the fp32 rounding of the key
+// and of the difference.  NaN (thr = cmin = +inf) compares false, which is right: a chunk of padding
+// columns holds no candidates; thr = +inf (empty list) gives -inf, everything passes.
+__device__ __forceinline__ float raw_limit(float thr, float cmin, float sc) {
+  const float rs = __frcp_rn(sc);
+  const float lim = (thr - cmin) * rs;
+  return lim - ((fabsf(thr) + fabsf(cmin)) * fabsf(rs) + fabsf(lim)) * 2e-7f;
+}
+
 // -------------------------------------------------- per-row (k+1)-smallest lists
 // Ranking key for row i over columns j:  t_ij = |y_j|^2 - 2 <x_i, y_j>
 // (d_ij^2 = |x_i|^2 + t_ij).  Each thread keeps its row's K smallest approximate
@@ -166,6 +179,7 @@ struct TopkEpi {
   const float* inv_a;
   const float* inv_b;
   const float* norm_b;
+  const float* cmin_b;     // per-chunk minima of norm_b (nullptr: no prefilter)
   float* keys;             // [2 * n_split][list_rows][K]   (list = 2 * split + half)
   int* cols;               // [2 * n_split][list_rows][K]   (-1 = empty)
   long long list_rows;     // rows covered by this launch (multiple of 128)
@@ -178,6 +192,7 @@ struct TopkEpi {
   // K-th key at that time >= that list's final K-th key >= the K-th smallest of the union.
   struct Row { float m2isr; float v[K]; int c[K]; float* mine; const volatile float* peer; };
   __device__ const float* colvec_ptr(int v) const { return v == 0 ? inv_b : norm_b; }
+  __device__ const float* cmin_ptr() const { return cmin_b; }
   __device__ void row_begin(Row& r, const ItemCoord&, long long a_row, int half, float* xchg) const {
     r.m2isr = -2.0f * inv_a[a_row];
 #pragma unroll
@@ -187,12 +202,20 @@ struct TopkEpi {
     *r.mine = kInf;
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
-                        long long b_row0, float* scratch) const {
-    // branch-free scan first: most chunks hold nothing below the row's current
-    // K-th smallest key
+                        long long b_row0, float* scratch, float cmin) const {
+    const float sc = cv[0][c0] * r.m2isr;   // -2 / (scale_a scale_b): one per tile (powers of two, exact)
+    const float thr = fminf(r.v[K - 1], *r.peer);
+    // Cheapest test first, on the raw accumulators (kernels that stage the chunk minima): a candidate
+    // needs |y_j|^2 + sc acc_j < thr, and |y_j|^2 >= cmin for the whole chunk — see raw_limit().
+    if (cmin > -kInf) {
+      float mx = f32(acc[0]);
+#pragma unroll
+      for (int j = 1; j < 32; ++j) mx = fmaxf(mx, f32(acc[j]));
+      if (!__any_sync(0xffffffffu, mx > raw_limit(thr, cmin, sc))) return;
+    }
+    // branch-free scan next: most chunks hold nothing below the row's current K-th smallest key
     float t[32];
     float g[4];                              // minimum of each 8-column group
-    const float sc = cv[0][c0] * r.m2isr;   // -2 / (scale_a scale_b): one per tile (powers of two, exact)
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       float ma = kInf, mb = kInf;
@@ -206,7 +229,6 @@ struct TopkEpi {
       g[h] = fminf(ma, mb);
     }
     const float tmin = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
-    const float thr = fminf(r.v[K - 1], *r.peer);
     if (__any_sync(0xffffffffu, tmin < thr)) {
       // some row of the warp takes new candidates.  Per 8-column group of the chunk that
       // holds one: each thread builds the bit mask of its qualifying columns, parks the 8
@@ -277,6 +299,7 @@ struct CountEpi {
   const float* norm_b;
   const float* b_lo;       // indexed by packed B row
   const float* b_hi;
+  const float* cmin_b;     // per-chunk minima of norm_b (nullptr: no prefilter)
   int32_t* col_count;      // [m], atomically incremented
   uint8_t* row_recall;     // [rows of this launch], relative to a_row_base
   uint8_t* row_cover;
@@ -289,6 +312,7 @@ struct CountEpi {
   __device__ const float* colvec_ptr(int v) const {
     return v == 0 ? inv_b : (v == 1 ? norm_b : (v == 2 ? b_hi : b_lo));
   }
+  __device__ const float* cmin_ptr() const { return cmin_b; }
   __device__ void row_begin(Row& r, const ItemCoord&, long long a_row, int, float*) const {
     r.m2isr = -2.0f * inv_a[a_row];
     r.nx = norm_a[a_row];
@@ -303,14 +327,23 @@ struct CountEpi {
     if (pos < list_cap) list[pos] = PairEntry{i, j_kind};
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
-                        long long b_row0, float*) const {
+                        long long b_row0, float*, float cmin) const {
     bool any_ref = false, any_cand = false;
     const float sc = cv[0][c0] * r.m2isr;   // -2 / (scale_a scale_b): one per tile (powers of two, exact)
+    // in_ref needs |y_j|^2 + sc acc_j < A_hi; with |y_j|^2 >= cmin over the chunk the per-column test
+    // of t is skipped unless the chunk's largest raw accumulator passes raw_limit().
+    if (cmin > -kInf) {
+      float mx = f32(acc[0]);
+#pragma unroll
+      for (int j = 1; j < 32; ++j) mx = fmaxf(mx, f32(acc[j]));
+      any_ref = mx > raw_limit(r.Ahi, cmin, sc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) any_ref |= (fmaf(f32(acc[j]), sc, cv[1][c0 + j]) < r.Ahi);
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float t = fmaf(f32(acc[j]), sc, cv[1][c0 + j]);
       const float u = fmaf(f32(acc[j]), sc, r.nx);
-      any_ref |= (t < r.Ahi);
       any_cand |= (u < cv[2][c0 + j]);
     }
     // Hits are rare (about k per row over the whole sweep).  A thread that has one

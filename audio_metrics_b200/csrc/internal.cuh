@@ -35,13 +35,13 @@ int option_engine_reserve_sms();  // amb_set_option("engine_reserve_sms")
 void* profile_begin(cudaStream_t stream);
 void profile_end(void* token, cudaStream_t stream, double alg_pairs, double exec_flops);
 
-// Layout of a packed blob (see packed.cuh): [hi plane][lo plane][inv_scale][norm][rho][row_exp].
+// Layout of a packed blob (see packed.cuh): [hi plane][lo plane][inv_scale][norm][rho][row_exp][cmin].
 struct PackedLayout {
   long long rows_pad;
   int kpad;
   int kb_count;
   long long plane_halfs;
-  size_t off_lo, off_inv, off_norm, off_rho, off_exp, bytes;
+  size_t off_lo, off_inv, off_norm, off_rho, off_exp, off_cmin, bytes;
 };
 PackedLayout packed_layout(long long n_rows, int d);
 
@@ -52,6 +52,7 @@ struct PackedPtrs {
   float* norm;
   float* rho;   // |x - hi(x)|, rounded up: what the single-pass filter's error band is built from
   int* row_exp; // binary exponent of each row's largest magnitude (scratch of the pack pass)
+  float* cmin;  // [rows_pad / 32] smallest squared norm of each 32-row chunk
   long long rows_pad;
   int kb_count;
 };
@@ -60,7 +61,7 @@ PackedPtrs packed_ptrs(void* blob, long long n_rows, int d);
 int launch_pack(cudaStream_t stream, const void* src, int dtype, long long ld, int d,
                 long long n_src_rows, const int* gather, long long n_valid, long long row0,
                 long long n_rows_out, __half* planes, long long plane_halfs, int kb_count,
-                float* inv_scale, float* norm, float* rho, int* row_exp);
+                float* inv_scale, float* norm, float* rho, int* row_exp, float* cmin);
 
 // Integer tensor-core Gram / column sums of an fp32 matrix (cov_tc.cu).
 size_t cov_tc_ws_bytes(long long n, int d);

@@ -114,9 +114,9 @@ int amb_kd_subsets(int dev, amb_stream_t stream, const void* F1, long long n1, l
   if ((rc = check_launch("kd_tables_kernel"))) return rc;
   const long long half = static_cast<long long>(S) * w.mp;
   if ((rc = launch_pack(st, F1, dtype, ld1, d, n1, w.gather, half, 0, half, p.planes, p.plane_halfs,
-                        p.kb_count, p.inv_scale, p.norm, p.rho, p.row_exp))) return rc;
+                        p.kb_count, p.inv_scale, p.norm, p.rho, p.row_exp, p.cmin))) return rc;
   if ((rc = launch_pack(st, F2, dtype, ld2, d, n2, w.gather + half, half, half, half, p.planes, p.plane_halfs,
-                        p.kb_count, p.inv_scale, p.norm, p.rho, p.row_exp))) return rc;
+                        p.kb_count, p.inv_scale, p.norm, p.rho, p.row_exp, p.cmin))) return rc;
 
   EngineGeom g{};
   g.a_planes = p.planes;

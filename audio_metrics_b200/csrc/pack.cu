@@ -151,10 +151,23 @@ pack_rows_kernel(const T* __restrict__ src, long long ld, int d, long long n_src
   }
 }
 
+// cmin[c] = smallest squared norm among packed rows [32 c, 32 c + 32): lets the radii / count
+// epilogues bound  |y|^2 - 2<x,y>  for a whole 32-column chunk from the raw accumulators alone.
+__global__ void chunk_min_norm_kernel(const float* __restrict__ norm, long long row0, long long n_rows_out,
+                                      float* __restrict__ cmin) {
+  const long long c = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c * 32 >= n_rows_out) return;
+  float v = norm[row0 + c * 32 + lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) cmin[row0 / 32 + c] = v;
+}
+
 int launch_pack(cudaStream_t stream, const void* src, int dtype, long long ld, int d,
                 long long n_src_rows, const int* gather, long long n_valid, long long row0,
                 long long n_rows_out, __half* planes, long long plane_halfs, int kb_count,
-                float* inv_scale, float* norm, float* rho, int* row_exp) {
+                float* inv_scale, float* norm, float* rho, int* row_exp, float* cmin) {
   if (n_rows_out <= 0) return 0;
   if (row0 % kRowPad != 0 || n_rows_out % kRowPad != 0)
     return set_error(AMB_ERR_ARG, "pack: row range must be whole 256-row tiles");
@@ -180,7 +193,10 @@ int launch_pack(cudaStream_t stream, const void* src, int dtype, long long ld, i
   } else {
     return set_error(AMB_ERR_ARG, "pack: dtype must be AMB_F32 or AMB_F64");
   }
-  return check_launch("pack_rows_kernel");
+  int rc = check_launch("pack_rows_kernel");
+  if (rc) return rc;
+  chunk_min_norm_kernel<<<static_cast<unsigned>((n_rows_out + 255) / 256), 256, 0, stream>>>(norm, row0, n_rows_out, cmin);
+  return check_launch("chunk_min_norm_kernel");
 }
 
 }  // namespace amb

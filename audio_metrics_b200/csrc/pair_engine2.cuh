@@ -41,6 +41,7 @@ constexpr int kSchedConsumers = 2 * (kEngineThreads / 32) - 1;   // every warp o
 template <int NCV>
 struct EngineSmem2T {
   alignas(128) float colvec[kCvSlots][NCV][kTileN];
+  alignas(32) float cvmin[kCvSlots][kTileN / 32];   // min |y|^2 of each 32-column chunk of the tile
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t peer_full[kMaxStages];
@@ -248,11 +249,14 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
         const int q = tile & (kCvSlots - 1);
         mbar_wait(&sh->cv_empty[q], ((tile / kCvSlots) & 1u) ^ 1u);   // the epilogue of four tiles ago
         if (elect_one()) {
-          mbar_expect_tx(&sh->cv_full[q], Epi::kColVecs * kTileN * 4);
+          const float* cm = epi.cmin_ptr();
+          mbar_expect_tx(&sh->cv_full[q], Epi::kColVecs * kTileN * 4 + (cm ? kTileN / 32 * 4 : 0));
 #pragma unroll
           for (int v = 0; v < Epi::kColVecs; ++v)
             bulk_g2s(sh->colvec[q][v], epi.colvec_ptr(v) + (b_rb_base + 2ll * ct) * kBlockRows, kTileN * 4,
                      &sh->cv_full[q]);
+          if (cm)
+            bulk_g2s(sh->cvmin[q], cm + (b_rb_base + 2ll * ct) * kBlockRows / 32, kTileN / 32 * 4, &sh->cv_full[q]);
         }
         ++tile;
         for (int j = 0; j < n_kp; ++j) {
@@ -378,7 +382,8 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
           uint32_t r[32];
           tmem_ld32(t_addr + c0, r);
           tmem_wait_ld();
-          epi.chunk(row, r, sh->colvec[q], c0, ct * kTileN + c0, b_row0 + c0, scratch);
+          epi.chunk(row, r, sh->colvec[q], c0, ct * kTileN + c0, b_row0 + c0, scratch,
+                    epi.cmin_ptr() ? sh->cvmin[q][c0 >> 5] : -__builtin_huge_valf());
         }
         tc_fence_before();
         __syncwarp();

@@ -409,7 +409,7 @@ static int run_engine(int mode, cudaStream_t st, int dev, EngineGeom g, const Ep
 template <int K>
 static int run_topk(cudaStream_t st, int dev, EngineGeom& g, const PackedPtrs& p, const KnnWs& w,
                     long long list_rows, long long a_row_base, double alg_pairs, int mode) {
-  TopkEpi<K> epi{p.inv_scale, p.inv_scale, p.norm, w.keys, w.cols, list_rows, a_row_base};
+  TopkEpi<K> epi{p.inv_scale, p.inv_scale, p.norm, p.cmin, w.keys, w.cols, list_rows, a_row_base};
   return run_engine(mode, st, dev, g, epi, "pair_engine<topk>", alg_pairs, w.n_unresolved + 16);   // zeroed with n_unresolved
 }
 
@@ -590,7 +590,7 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   }
   g.lbo_bytes = 128;
   g.sbo_bytes = 512;
-  CountEpi epi{pr.inv_scale, pr.norm, a_lo, a_hi, pc.inv_scale, pc.norm, b_lo, b_hi, col_count, row_recall,
+  CountEpi epi{pr.inv_scale, pr.norm, a_lo, a_hi, pc.inv_scale, pc.norm, b_lo, b_hi, pc.cmin, col_count, row_recall,
                row_cover, row0, row0 + nrows, list, list_count, static_cast<unsigned long long>(cap)};
   if ((rc = run_engine(mode, st, dev, g, epi, "pair_engine<count>", static_cast<double>(nrows) * m,
                        reinterpret_cast<int*>(q + 192)))) return rc;   // inside the zeroed 512-byte header

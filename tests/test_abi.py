@@ -34,9 +34,9 @@ def test_ctypes_table_matches_header():
 
 def test_size_queries_need_no_gpu():
     L = _lib.lib()
-    # packed blob: rows padded to 256, k to 32, 4 B/element + 16 B/row (scale, norm, rho, exponent)
-    assert L.amb_packed_bytes(1000, 512) == 1024 * 512 * 4 + 1024 * 16
-    assert L.amb_packed_bytes(1, 10) == 256 * 32 * 4 + 256 * 16
+    # packed blob: rows padded to 256, k to 32, 4 B/element + 16 B/row (scale, norm, rho, exponent) + 4 B per 32 rows (chunk minimum norm), rounded to 256
+    assert L.amb_packed_bytes(1000, 512) == 1024 * 512 * 4 + 1024 * 16 + 256
+    assert L.amb_packed_bytes(1, 10) == 256 * 32 * 4 + 256 * 16 + 256
     assert L.amb_packed_bytes(-1, 4) == 0
     assert L.amb_cov_ws_bytes(100000, 512) > 0
     assert L.amb_frechet_ws_bytes(3, 512) >= 3 * 3 * 512 * 512 * 8
