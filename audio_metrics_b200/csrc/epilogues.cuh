@@ -25,13 +25,14 @@ struct DumpEpi {
   struct Row { float isr; long long a_row; float sum; };
   __device__ const float* colvec_ptr(int) const { return inv_b; }
   __device__ const float* cmin_ptr() const { return nullptr; }
+  __device__ const float* cmax_ptr() const { return nullptr; }
   __device__ void row_begin(Row& r, const ItemCoord&, long long a_row, int, float*) const {
     r.isr = inv_a[a_row];
     r.a_row = a_row;
     r.sum = 0.f;
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
-                        long long b_row0, float*, float) const {
+                        long long b_row0, float*, float, float) const {
     if (r.a_row >= na) return;
     const float sc = cv[0][c0] * r.isr;
     if (checksum_only) {
@@ -70,6 +71,7 @@ struct KdEpi {
   struct Row { double sum; double gr; float na; int row_in_problem; bool valid; bool sym; };
   __device__ const float* colvec_ptr(int) const { return inv_b; }
   __device__ const float* cmin_ptr() const { return nullptr; }
+  __device__ const float* cmax_ptr() const { return nullptr; }
   __device__ void row_begin(Row& r, const ItemCoord& c, long long a_row, int, float*) const {
     r.row_in_problem = c.rt * kTileM + static_cast<int>(a_row % kTileM);
     r.valid = r.row_in_problem < m_valid;
@@ -94,7 +96,7 @@ struct KdEpi {
     }
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0,
-                        int col0, long long b_row0, float*, float) const {
+                        int col0, long long b_row0, float*, float, float) const {
     if (!r.valid) return;
     const bool edge = (col0 + 32 > m_valid) || (r.sym && col0 <= r.row_in_problem && r.row_in_problem < col0 + 32);
     if (!edge && kernel_type == AMB_KERNEL_POLY && degree == 3) {
@@ -193,6 +195,7 @@ struct TopkEpi {
   struct Row { float m2isr; float v[K]; int c[K]; float* mine; const volatile float* peer; };
   __device__ const float* colvec_ptr(int v) const { return v == 0 ? inv_b : norm_b; }
   __device__ const float* cmin_ptr() const { return cmin_b; }
+  __device__ const float* cmax_ptr() const { return nullptr; }
   __device__ void row_begin(Row& r, const ItemCoord&, long long a_row, int half, float* xchg) const {
     r.m2isr = -2.0f * inv_a[a_row];
 #pragma unroll
@@ -202,7 +205,7 @@ struct TopkEpi {
     *r.mine = kInf;
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
-                        long long b_row0, float* scratch, float cmin) const {
+                        long long b_row0, float* scratch, float cmin, float) const {
     const float sc = cv[0][c0] * r.m2isr;   // -2 / (scale_a scale_b): one per tile (powers of two, exact)
     const float thr = fminf(r.v[K - 1], *r.peer);
     // Cheapest test first, on the raw accumulators (kernels that stage the chunk minima): a candidate
@@ -300,6 +303,7 @@ struct CountEpi {
   const float* b_lo;       // indexed by packed B row
   const float* b_hi;
   const float* cmin_b;     // per-chunk minima of norm_b (nullptr: no prefilter)
+  const float* cmax_bhi;   // per-chunk maxima of b_hi (nullptr: no prefilter)
   int32_t* col_count;      // [m], atomically incremented
   uint8_t* row_recall;     // [rows of this launch], relative to a_row_base
   uint8_t* row_cover;
@@ -313,6 +317,7 @@ struct CountEpi {
     return v == 0 ? inv_b : (v == 1 ? norm_b : (v == 2 ? b_hi : b_lo));
   }
   __device__ const float* cmin_ptr() const { return cmin_b; }
+  __device__ const float* cmax_ptr() const { return cmax_bhi; }
   __device__ void row_begin(Row& r, const ItemCoord&, long long a_row, int, float*) const {
     r.m2isr = -2.0f * inv_a[a_row];
     r.nx = norm_a[a_row];
@@ -327,24 +332,25 @@ struct CountEpi {
     if (pos < list_cap) list[pos] = PairEntry{i, j_kind};
   }
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
-                        long long b_row0, float*, float cmin) const {
+                        long long b_row0, float*, float cmin, float cmax) const {
     bool any_ref = false, any_cand = false;
     const float sc = cv[0][c0] * r.m2isr;   // -2 / (scale_a scale_b): one per tile (powers of two, exact)
-    // in_ref needs |y_j|^2 + sc acc_j < A_hi; with |y_j|^2 >= cmin over the chunk the per-column test
-    // of t is skipped unless the chunk's largest raw accumulator passes raw_limit().
+    // Both tests first on the chunk as a whole, from the largest raw accumulator (raw_limit()):
+    //   in_ref  needs |y_j|^2 + sc acc_j < A_hi,   and |y_j|^2 >= cmin over the chunk;
+    //   in_cand needs |x_i|^2 + sc acc_j < B_hi_j, and B_hi_j <= cmax over the chunk.
+    // Kernels that do not stage the chunk arrays (cmin = -inf) test every column as before.
     if (cmin > -kInf) {
       float mx = f32(acc[0]);
 #pragma unroll
       for (int j = 1; j < 32; ++j) mx = fmaxf(mx, f32(acc[j]));
       any_ref = mx > raw_limit(r.Ahi, cmin, sc);
+      any_cand = mx > raw_limit(cmax, r.nx, sc);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) any_ref |= (fmaf(f32(acc[j]), sc, cv[1][c0 + j]) < r.Ahi);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float u = fmaf(f32(acc[j]), sc, r.nx);
-      any_cand |= (u < cv[2][c0 + j]);
+      for (int j = 0; j < 32; ++j) {
+        any_ref |= (fmaf(f32(acc[j]), sc, cv[1][c0 + j]) < r.Ahi);
+        any_cand |= (fmaf(f32(acc[j]), sc, r.nx) < cv[2][c0 + j]);
+      }
     }
     // Hits are rare (about k per row over the whole sweep).  A thread that has one
     // rebuilds its comparisons as bit masks and walks the set bits on its own:

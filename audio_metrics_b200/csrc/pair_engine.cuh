@@ -116,10 +116,12 @@ __device__ __forceinline__ ItemCoord decode_item(const EngineGeom& g, int item) 
 //                    float* xchg /*2 floats shared by the two threads of this tile row, or nullptr;
 //                                  both threads pass a 64-thread barrier after row_begin*/) const;
 //     const float* cmin_ptr() const;                 // per-32-row chunk minima of |y|^2 (packed.cuh), or nullptr
+//     const float* cmax_ptr() const;                 // a second per-32-row chunk array (maxima of a threshold), or nullptr
 //     void chunk(Row&, const uint32_t (&acc)[32], const float (*cv)[kTileN], int col_in_tile,
 //                int col_in_problem, long long b_row0 /*packed B row of chunk column 0*/,
 //                float* scratch /*kScratchFloats floats private to this thread, or nullptr*/,
-//                float cmin /*min |y|^2 over the chunk's 32 columns if the kernel stages it, else -inf*/) const;
+//                float cmin /*min |y|^2 over the chunk's 32 columns if the kernel stages it, else -inf*/,
+//                float cmax /*the chunk's value of cmax_ptr() if staged, else +inf*/) const;
 //     void row_end(Row&, const ItemCoord&, int item, long long a_row, int quarter, int lane,
 //                  int half /*which 128 columns of every tile this thread swept*/) const;
 //   };
@@ -162,7 +164,7 @@ __device__ __forceinline__ void epilogue_role(const EngineGeom& g, const Epi& ep
         uint32_t r[32];
         tmem_ld32(t_addr + c0, r);
         tmem_wait_ld();
-        epi.chunk(row, r, sh->colvec[acc], c0, ct * kTileN + c0, b_row0 + c0, scratch, -__builtin_huge_valf());
+        epi.chunk(row, r, sh->colvec[acc], c0, ct * kTileN + c0, b_row0 + c0, scratch, -__builtin_huge_valf(), __builtin_huge_valf());
       }
       tc_fence_before();
       __syncwarp();

@@ -42,6 +42,7 @@ template <int NCV>
 struct EngineSmem2T {
   alignas(128) float colvec[kCvSlots][NCV][kTileN];
   alignas(32) float cvmin[kCvSlots][kTileN / 32];   // min |y|^2 of each 32-column chunk of the tile
+  alignas(32) float cvmax[kCvSlots][kTileN / 32];   // the epilogue's second per-chunk array
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t peer_full[kMaxStages];
@@ -250,13 +251,16 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
         mbar_wait(&sh->cv_empty[q], ((tile / kCvSlots) & 1u) ^ 1u);   // the epilogue of four tiles ago
         if (elect_one()) {
           const float* cm = epi.cmin_ptr();
-          mbar_expect_tx(&sh->cv_full[q], Epi::kColVecs * kTileN * 4 + (cm ? kTileN / 32 * 4 : 0));
+          const float* cx = epi.cmax_ptr();
+          mbar_expect_tx(&sh->cv_full[q], Epi::kColVecs * kTileN * 4 + (cm ? kTileN / 32 * 4 : 0) + (cx ? kTileN / 32 * 4 : 0));
 #pragma unroll
           for (int v = 0; v < Epi::kColVecs; ++v)
             bulk_g2s(sh->colvec[q][v], epi.colvec_ptr(v) + (b_rb_base + 2ll * ct) * kBlockRows, kTileN * 4,
                      &sh->cv_full[q]);
           if (cm)
             bulk_g2s(sh->cvmin[q], cm + (b_rb_base + 2ll * ct) * kBlockRows / 32, kTileN / 32 * 4, &sh->cv_full[q]);
+          if (cx)
+            bulk_g2s(sh->cvmax[q], cx + (b_rb_base + 2ll * ct) * kBlockRows / 32, kTileN / 32 * 4, &sh->cv_full[q]);
         }
         ++tile;
         for (int j = 0; j < n_kp; ++j) {
@@ -383,7 +387,8 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
           tmem_ld32(t_addr + c0, r);
           tmem_wait_ld();
           epi.chunk(row, r, sh->colvec[q], c0, ct * kTileN + c0, b_row0 + c0, scratch,
-                    epi.cmin_ptr() ? sh->cvmin[q][c0 >> 5] : -__builtin_huge_valf());
+                    epi.cmin_ptr() ? sh->cvmin[q][c0 >> 5] : -__builtin_huge_valf(),
+                    epi.cmax_ptr() ? sh->cvmax[q][c0 >> 5] : __builtin_huge_valf());
         }
         tc_fence_before();
         __syncwarp();

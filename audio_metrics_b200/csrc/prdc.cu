@@ -206,6 +206,17 @@ knn_bruteforce_kernel(const T* __restrict__ X, long long ld, int d, long long n,
   }
 }
 
+// out[c] = max of v[32 c .. 32 c + 31]
+__global__ void chunk_max_kernel(const float* __restrict__ v, long long n, float* __restrict__ out) {
+  const long long c = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c * 32 >= n) return;
+  float x = v[c * 32 + lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+  if (lane == 0) out[c] = x;
+}
+
 // ---------------------------------------------------------- counts: thresholds
 __global__ void prdc_thresholds_kernel(const float* __restrict__ norm, const float* __restrict__ rho,
                                        bool single_pass, const float* __restrict__ radii,
@@ -519,7 +530,7 @@ long long amb_prdc_list_cap(long long n_ref, long long m) {
 size_t amb_prdc_ws_bytes(long long n_ref, long long m) {
   if (n_ref <= 0 || m <= 0) return 0;
   const long long rp = round_up_ll(n_ref, kRowPad), cp = round_up_ll(m, kRowPad);
-  return static_cast<size_t>(round_up_ll((2 * rp + 2 * cp) * 4, 256) + 512 + amb_prdc_list_cap(n_ref, m) * 8);
+  return static_cast<size_t>(round_up_ll((2 * rp + 2 * cp + cp / 32) * 4, 256) + 512 + amb_prdc_list_cap(n_ref, m) * 8);
 }
 
 int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, const void* packed_ref,
@@ -547,7 +558,8 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   float* a_hi = a_lo + pr.rows_pad;
   float* b_lo = a_hi + pr.rows_pad;
   float* b_hi = b_lo + pc.rows_pad;
-  uint8_t* q = b + round_up_ll((2 * pr.rows_pad + 2 * pc.rows_pad) * 4, 256);
+  float* cmax_bhi = b_hi + pc.rows_pad;   // [cols_pad / 32] chunk maxima of b_hi
+  uint8_t* q = b + round_up_ll((2 * pr.rows_pad + 2 * pc.rows_pad + pc.rows_pad / 32) * 4, 256);
   unsigned long long* list_count = reinterpret_cast<unsigned long long*>(q);
   float* max_ref = reinterpret_cast<float*>(q + 64);
   float* max_cand = reinterpret_cast<float*>(q + 128);
@@ -570,6 +582,8 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   prdc_thresholds_kernel<<<static_cast<unsigned>((pc.rows_pad + 255) / 256), 256, 0, st>>>(
       pc.norm, pc.rho, sp, r_cand, m, pc.rows_pad, max_ref, b_lo, b_hi);
   if ((rc = check_launch("prdc_thresholds_kernel"))) return rc;
+  chunk_max_kernel<<<static_cast<unsigned>((pc.rows_pad + 255) / 256), 256, 0, st>>>(b_hi, pc.rows_pad, cmax_bhi);
+  if ((rc = check_launch("chunk_max_kernel"))) return rc;
 
   EngineGeom g{};
   g.a_planes = pr.planes;
@@ -590,7 +604,7 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   }
   g.lbo_bytes = 128;
   g.sbo_bytes = 512;
-  CountEpi epi{pr.inv_scale, pr.norm, a_lo, a_hi, pc.inv_scale, pc.norm, b_lo, b_hi, pc.cmin, col_count, row_recall,
+  CountEpi epi{pr.inv_scale, pr.norm, a_lo, a_hi, pc.inv_scale, pc.norm, b_lo, b_hi, pc.cmin, cmax_bhi, col_count, row_recall,
                row_cover, row0, row0 + nrows, list, list_count, static_cast<unsigned long long>(cap)};
   if ((rc = run_engine(mode, st, dev, g, epi, "pair_engine<count>", static_cast<double>(nrows) * m,
                        reinterpret_cast<int*>(q + 192)))) return rc;   // inside the zeroed 512-byte header
