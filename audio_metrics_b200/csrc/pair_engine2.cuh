@@ -11,8 +11,9 @@
 //     256 columns, so the epilogue (one thread = tile row x column half) is unchanged.
 //
 // Hand-shakes (L = leader CTA, rank 0; P = peer CTA, rank 1):
-//   full[s]            local   TMA bytes of this CTA's slot s landed
-//   peer_full[s]       in L    P's relay warp saw P.full[s] and arrived remotely
+//   full[s]            local   TMA bytes of this CTA's slot s landed; in L the same barrier also counts
+//                              the remote arrive of P's relay warp ("P.full[s] completed"), so the
+//                              MMA issuer makes one wait per slot for both halves of the B tile
 //   empty[s]           local   L's MMA commit, multicast to both CTAs: slot s may be refilled
 //   a_full/peer_a_full, a_empty   the same three for the resident A panel
 //   tmem_full[acc]     local   L's MMA commit, multicast: accumulator acc is complete
@@ -45,7 +46,6 @@ struct EngineSmem2T {
   alignas(32) float cvmax[kCvSlots][kTileN / 32];   // the epilogue's second per-chunk array
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t peer_full[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t pair_tmem_empty[2];
   uint64_t cv_full[kCvSlots];
@@ -193,9 +193,8 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
-      mbar_init(&sh->full[s], 1);
+      mbar_init(&sh->full[s], leader ? 2 : 1);   // own producer (+ bytes), and in L the peer's relay
       mbar_init(&sh->empty[s], 1);
-      mbar_init(&sh->peer_full[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sh->tmem_full[a], 1);
@@ -298,8 +297,7 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kTileN;
           for (int j = 0; j < n_kp; ++j) {
-            mbar_wait(&sh->full[s], ph);
-            mbar_wait_cluster(&sh->peer_full[s], ph);
+            mbar_wait(&sh->full[s], ph);        // both CTAs' halves of the slot have landed
             tc_fence_after();
             if (elect_one()) {
               const uint64_t a_d = a_desc0 + static_cast<uint64_t>(2 * j * (kChunkBytes >> 4));
@@ -338,7 +336,7 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
         for (int ct = c.ct_begin; ct < c.ct_end; ++ct) {
           for (int j = 0; j < n_kp; ++j) {
             mbar_wait(&sh->full[s], ph);
-            if (elect_one()) mbar_arrive_cluster(map_to_cta(&sh->peer_full[s], 0));
+            if (elect_one()) mbar_arrive_cluster(map_to_cta(&sh->full[s], 0));
             if (++s == n_stages) { s = 0; ph ^= 1; }
           }
         }
