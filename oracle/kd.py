@@ -59,8 +59,9 @@ def draw_subset_indices(n1, n2, m, subsets=KID_SUBSETS, seed=RNG_SEED):
 
 def kernel_distance(f1, f2, subsets=KID_SUBSETS, subset_size=KID_SUBSET_SIZE, seed=RNG_SEED,
                     degree=KID_DEGREE, gamma=None, coef0=KID_COEF0, compute_dtype=None,
-                    return_mmds=False):
-    """kd.py:127-194 kid_features_to_metric with the polynomial kernel.
+                    return_mmds=False, kernel_type="polynomial", sigma=10.0):
+    """kd.py:127-194 kid_features_to_metric with the polynomial kernel (or, kernel_type="rbf",
+    the RBF kernel of kd.py:86-109 that only the keyword interface reaches).
 
     f1 = candidate features, f2 = reference features (audio_metrics.py:260 passes
     (cand, ref)).  Arithmetic runs in the input dtype (float32 for embedder output),
@@ -81,9 +82,12 @@ def kernel_distance(f1, f2, subsets=KID_SUBSETS, subset_size=KID_SUBSET_SIZE, se
     for i in range(subsets):
         a = f1[idx[i, 0]]
         b = f2[idx[i, 1]]
-        k11 = polynomial_kernel(a, a, degree, gamma, coef0)   # kd.py:120
-        k22 = polynomial_kernel(b, b, degree, gamma, coef0)   # kd.py:121
-        k12 = polynomial_kernel(a, b, degree, gamma, coef0)   # kd.py:122
+        if kernel_type == "rbf":
+            k11, k22, k12 = rbf_kernel(a, a, sigma), rbf_kernel(b, b, sigma), rbf_kernel(a, b, sigma)
+        else:
+            k11 = polynomial_kernel(a, a, degree, gamma, coef0)   # kd.py:120
+            k22 = polynomial_kernel(b, b, degree, gamma, coef0)   # kd.py:121
+            k12 = polynomial_kernel(a, b, degree, gamma, coef0)   # kd.py:122
         mmds[i] = mmd2_unbiased(k11, k12, k22)                # kd.py:124
     out = {"kernel_distance_mean": float(np.mean(mmds)), "kernel_distance_std": float(np.std(mmds))}
     if return_mmds:

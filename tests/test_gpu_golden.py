@@ -69,3 +69,25 @@ def test_cuda_apa_and_rank1_golden(cuda_device):
     assert frechet_distance(A, B) == pytest.approx(r["fad"], rel=1e-5)
     scale = float(A.cov.trace()) * 2
     assert abs(frechet_distance(A, A) - r["fad_self"]) < 1e-6 * scale
+
+
+def test_kd_keyword_variants_match_reference(cuda_device):
+    """The keyword interface of kid_features_to_metric (kd.py:127-194: RBF kernel, polynomial
+    parameters, subset count / size, seed) against the unmodified reference's values."""
+    import json
+    from pathlib import Path
+
+    import torch
+
+    from audio_metrics_b200.metrics.kd import kid_features_to_metric
+    from audio_metrics_b200.synth import make_sets_numpy
+
+    g = json.loads((Path(__file__).parent / "golden" / "golden_kd_variants.json").read_text())
+    i = g["input"]
+    ref, cand = make_sets_numpy(i["n_ref"], i["n_cand"], i["d"], seed=i["seed"])
+    for name, v in g["variants"].items():
+        got = kid_features_to_metric(torch.from_numpy(cand), torch.from_numpy(ref), **v["kwargs"])
+        for key in ("kernel_distance_mean", "kernel_distance_std"):
+            want64, want32 = v["reference_f64"][key], v["reference_f32"][key]
+            assert got[key] == pytest.approx(want64, rel=1e-4, abs=1e-9), (name, key)      # north-star tolerance
+            assert abs(got[key] - want32) <= 2 * abs(want32 - want64) + 1e-4 * abs(want64) + 1e-9, (name, key)

@@ -121,3 +121,28 @@ def test_prdc_oracle_identities():
     same = oracle.prdc(x, x.copy(), 5, dist=cdist_exact)
     assert same["precision"] == 1.0 and same["recall"] == 1.0 and same["coverage"] == 1.0
     assert same["density"] == pytest.approx(1.0)
+
+
+def test_kd_keyword_variants_match_reference_goldens():
+    """kd.py:127-194 keyword interface (RBF kernel, degree/gamma/coef0, subset count/size, seed):
+    the oracle against values produced by the unmodified reference (tests/golden/make_golden_kd.py)."""
+    import json
+    from pathlib import Path
+
+    from audio_metrics_b200.synth import make_sets_numpy
+
+    g = json.loads((Path(__file__).parent / "golden" / "golden_kd_variants.json").read_text())
+    i = g["input"]
+    ref, cand = make_sets_numpy(i["n_ref"], i["n_cand"], i["d"], seed=i["seed"])
+    for name, v in g["variants"].items():
+        kw = v["kwargs"]
+        args = dict(subsets=kw.get("kid_subsets", 100), subset_size=kw.get("kid_subset_size", 1000),
+                    seed=kw.get("rng_seed", 1234), degree=kw.get("kid_degree", 3), gamma=kw.get("kid_gamma"),
+                    coef0=kw.get("kid_coef0", 1), kernel_type=kw.get("kernel_type", "polynomial"),
+                    sigma=kw.get("kid_sigma", 10.0))
+        got64 = oracle.kernel_distance(cand, ref, compute_dtype=np.float64, **args)
+        for key in ("kernel_distance_mean", "kernel_distance_std"):
+            assert got64[key] == pytest.approx(v["reference_f64"][key], rel=1e-9, abs=1e-15), (name, key)
+        got32 = oracle.kernel_distance(cand, ref, **args)
+        for key in ("kernel_distance_mean", "kernel_distance_std"):
+            assert got32[key] == pytest.approx(v["reference_f32"][key], rel=5e-3, abs=2e-8), (name, key)
