@@ -15,6 +15,7 @@ _lib = None
 
 AMB_F32, AMB_F64 = 0, 1
 AMB_KERNEL_POLY, AMB_KERNEL_RBF = 0, 1
+AMB_MMD_UNBIASED, AMB_MMD_BIASED, AMB_MMD_USTAT, AMB_MMD_UNIT_DIAGONAL = 0, 1, 2, 4
 AMB_ERR_ARG, AMB_ERR_CUDA, AMB_ERR_WS, AMB_ERR_NUMERIC = -1, -2, -3, -4
 
 _vp, _i, _ll, _sz, _dbl = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.c_double
@@ -25,6 +26,7 @@ SIGNATURES = {
     "amb_last_error": (C.c_char_p, []),
     "amb_launch_count": (_ll, []),
     "amb_set_option": (_i, [C.c_char_p, _i]),
+    "amb_get_option": (_i, [C.c_char_p]),
     "amb_profile_enable": (_i, [_i]),
     "amb_profile_read": (_i, [_vp]),
     "amb_cov_ws_bytes": (_sz, [_ll, _i]),
@@ -37,11 +39,14 @@ SIGNATURES = {
     "amb_pack": (_i, [_i, _vp, _vp, _i, _ll, _i, _ll, _vp]),
     "amb_kd_ws_bytes": (_sz, [_i, _i, _i]),
     "amb_kd_subsets": (_i, [_i, _vp, _vp, _ll, _ll, _vp, _ll, _ll, _i, _i, _vp, _i, _i, _i, _dbl, _dbl, _i,
-                            _dbl, _vp, _vp, _vp, _sz]),
+                            _dbl, _i, _vp, _vp, _vp, _sz]),
     "amb_knn_ws_bytes": (_sz, [_ll, _ll, _i, _i]),
-    "amb_knn_radii": (_i, [_i, _vp, _vp, _i, _ll, _vp, _ll, _i, _ll, _ll, _i, _vp, _vp, _sz]),
+    "amb_knn_radii": (_i, [_i, _vp, _vp, _i, _ll, _vp, _ll, _i, _ll, _ll, _i, _vp, _vp, _vp, _sz]),
     "amb_prdc_ws_bytes": (_sz, [_ll, _ll]),
+    "amb_prdc_ws_bytes_cap": (_sz, [_ll, _ll, _ll]),
+    "amb_prdc_ws_list_cap": (_ll, [_ll, _ll, _sz]),
     "amb_prdc_list_cap": (_ll, [_ll, _ll]),
+    "amb_prdc_counts_exact": (_i, [_i, _vp, _vp, _ll, _ll, _vp, _vp, _ll, _ll, _vp, _i, _i, _ll, _ll, _vp, _vp, _vp]),
     "amb_prdc_counts": (_i, [_i, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _i, _i, _ll, _ll,
                              _vp, _vp, _vp, _vp, _vp, _sz]),
     "amb_prdc_reduce": (_i, [_i, _vp, _vp, _ll, _vp, _vp, _ll, _vp]),
@@ -131,3 +136,26 @@ def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
 
 def launch_count() -> int:
     return int(lib().amb_launch_count())
+
+
+class options:
+    """``with options(fad_method=1, engine_passes=3): ...`` — set process-wide library options
+    (amb_set_option) for the duration of a block and restore the previous values.  For tests and
+    A/B measurements; the options are not meant to be toggled around calls in production."""
+
+    def __init__(self, **values):
+        self.values = values
+        self.saved = {}
+
+    def __enter__(self):
+        L = lib()
+        for name, v in self.values.items():
+            self.saved[name] = L.amb_get_option(name.encode())
+            check(L.amb_set_option(name.encode(), int(v)))
+        return self
+
+    def __exit__(self, *exc):
+        L = lib()
+        for name, v in self.saved.items():
+            L.amb_set_option(name.encode(), int(v))
+        return False

@@ -11,10 +11,8 @@ import torch
 from . import _lib
 from .data import AudioMetricsData
 from .embedders import DEFAULT_EMBEDDER, EMBEDDERS
-from .metrics.apa import apa, apa_compute_d_x_xp
-from .metrics.fad import frechet_distance
-from .metrics.kd import kernel_distance
-from .metrics.prdc import prdc
+from .dist import evaluate_containers
+from .metrics.apa import _apa
 from .mix import DEFAULT_MIX_FUNCTION, MIX_FUNCTIONS
 from .pipeline import ItemCategory, embedding_pipeline
 from .projection import IncrementalPCA
@@ -164,20 +162,25 @@ class AudioMetrics:
             raise ValueError("No apa candidate embeddings were computed")
         if self.stems_mode:
             stem_ref, stem_cand = self.ensure_stem_projection(stem_ref, stem_cand)
+        apa_sets = None
         if self.need_apa:
             apa_ref, apa_anti, apa_cand = self.ensure_mix_projection(apa_ref, apa_anti, apa_cand)
-            if self.apa_d_x_xp is None:
-                self.apa_d_x_xp = apa_compute_d_x_xp(apa_ref, apa_anti)
+            apa_sets = (apa_cand, apa_ref, apa_anti, self.apa_d_x_xp)       # :251-252: d_x_xp cached per reference
+        # One fused, asynchronous schedule with a single read-back (dist.py) instead of the
+        # reference's one call and one host synchronisation per metric (:254-272); under
+        # torch.distributed the containers hold this rank's rows and the step is row-sharded.
+        fused = tuple(m for m in ("fad", "kd", "prdc") if m in self.metrics) if self.stems_mode else ()
+        res = evaluate_containers(stem_ref if fused else None, stem_cand if fused else None, fused,
+                                  nearest_k=None, apa=apa_sets)   # k = max(1, min(10, n_ref, n_cand)), :263
         result = {}
-        if "fad" in self.metrics:
-            result["fad"] = frechet_distance(stem_cand, stem_ref)
-        if "kd" in self.metrics:
-            result.update(kernel_distance(stem_cand, stem_ref))
-        if "prdc" in self.metrics:
-            k = max(1, min(10, len(stem_ref), len(stem_cand)))
-            result.update(prdc(stem_ref, stem_cand, k))
+        for key in ("fad", "kernel_distance_mean", "kernel_distance_std", "precision", "recall", "density",
+                    "coverage"):
+            if key in res:
+                result[key] = res[key]
         if self.need_apa:
-            result["apa"] = apa(apa_cand, apa_ref, apa_anti, self.apa_d_x_xp)
+            if self.apa_d_x_xp is None:
+                self.apa_d_x_xp = res["_d_x_xp"]
+            result["apa"] = _apa(res["_d_y_x"], res["_d_y_xp"], self.apa_d_x_xp)      # apa.py:22-32
         return result
 
     # ----------------------------------------------------------------- registries

@@ -2,6 +2,7 @@
 // debug dot-matrix entry point.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -70,10 +71,44 @@ int sm_count(int dev) {
   return n;
 }
 
-static std::atomic<int> g_opt_jacobi_block{0}, g_opt_fad_ctas{0}, g_opt_reserve{0};
-int option_jacobi_block() { return g_opt_jacobi_block.load(std::memory_order_relaxed); }
-int option_fad_ctas() { return g_opt_fad_ctas.load(std::memory_order_relaxed); }
-int option_engine_reserve_sms() { return g_opt_reserve.load(std::memory_order_relaxed); }
+struct OptDef { const char* name; const char* env; int dflt; int lo, hi; };
+static const OptDef kOptDefs[kOptCount] = {
+    {"jacobi_block", "AMB_JACOBI_BS", 0, 0, 16},
+    {"fad_ctas", "AMB_FAD_CTAS", 0, 0, 4096},
+    {"engine_reserve_sms", "AMB_RESERVE_SMS", 0, 0, 128},
+    {"fad_method", "AMB_FAD_METHOD", 0, 0, 1},
+    {"engine_passes", "AMB_PASSES", 0, 0, 3},
+    {"engine_cta2", "AMB_CTA2", -1, -1, 1},
+    {"engine_static", "AMB_SCHED", 0, 0, 1},
+    {"engine_stages", "AMB_STAGES", 0, 0, 8},
+    {"engine_grid", "AMB_GRID", 0, 0, 4096},
+    {"tail_split", "AMB_TAIL_SPLIT", 0, 0, 64},
+    {"topk_split", "AMB_TOPK_SPLIT", 0, 0, 64},
+    {"count_split", "AMB_COUNT_SPLIT", 0, 0, 64},
+    {"debug_single", "AMB_DEBUG_SINGLE", 0, 0, 2},
+    {"cov_dfma", "AMB_COV", 0, 0, 1},
+    {"fad_factor_eig", "AMB_FAD_FACTOR", 0, 0, 1},
+    {"jacobi_flat", "AMB_JACOBI", 0, 0, 1},
+    {"fad_debug", "AMB_FAD_DEBUG", 0, 0, 1},
+};
+static std::atomic<int> g_opts[kOptCount];
+static std::once_flag g_opts_once;
+static void init_options() {
+  for (int i = 0; i < kOptCount; ++i) {
+    int v = kOptDefs[i].dflt;
+    if (const char* e = getenv(kOptDefs[i].env)) {
+      // numeric values as given; a word ("static", "dfma", "eig", "flat") switches the option on
+      if ((e[0] >= '0' && e[0] <= '9') || e[0] == '-') v = atoi(e);
+      else if (e[0]) v = 1;
+      if (v < kOptDefs[i].lo || v > kOptDefs[i].hi) v = kOptDefs[i].dflt;
+    }
+    g_opts[i].store(v, std::memory_order_relaxed);
+  }
+}
+int option(Opt o) {
+  std::call_once(g_opts_once, init_options);
+  return g_opts[o].load(std::memory_order_relaxed);
+}
 
 struct ProfRec { cudaEvent_t e0, e1; double pairs, flops; };
 static std::mutex g_prof_mu;
@@ -142,23 +177,24 @@ const char* amb_last_error(void) { return g_err; }
 long long amb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int amb_set_option(const char* name, int value) {
-  if (name && strcmp(name, "jacobi_block") == 0) {
-    if (value != 0 && value != 4 && value != 8 && value != 16)
+  std::call_once(g_opts_once, init_options);
+  for (int i = 0; name && i < kOptCount; ++i) {
+    if (strcmp(name, kOptDefs[i].name) != 0) continue;
+    if (value < kOptDefs[i].lo || value > kOptDefs[i].hi)
+      return set_error(AMB_ERR_ARG, "amb_set_option: %s must be in [%d, %d]", name, kOptDefs[i].lo, kOptDefs[i].hi);
+    if (i == kOptJacobiBlock && value != 0 && value != 4 && value != 8 && value != 16)
       return set_error(AMB_ERR_ARG, "amb_set_option: jacobi_block must be 0, 4, 8 or 16");
-    g_opt_jacobi_block.store(value);
-    return AMB_OK;
-  }
-  if (name && strcmp(name, "fad_ctas") == 0) {
-    if (value < 0) return set_error(AMB_ERR_ARG, "amb_set_option: fad_ctas must be >= 0");
-    g_opt_fad_ctas.store(value);
-    return AMB_OK;
-  }
-  if (name && strcmp(name, "engine_reserve_sms") == 0) {
-    if (value < 0 || value > 128) return set_error(AMB_ERR_ARG, "amb_set_option: engine_reserve_sms must be in [0, 128]");
-    g_opt_reserve.store(value);
+    g_opts[i].store(value, std::memory_order_relaxed);
     return AMB_OK;
   }
   return set_error(AMB_ERR_ARG, "amb_set_option: unknown option '%s'", name ? name : "(null)");
+}
+
+int amb_get_option(const char* name) {
+  std::call_once(g_opts_once, init_options);
+  for (int i = 0; name && i < kOptCount; ++i)
+    if (strcmp(name, kOptDefs[i].name) == 0) return g_opts[i].load(std::memory_order_relaxed);
+  return set_error(AMB_ERR_ARG, "amb_get_option: unknown option '%s'", name ? name : "(null)");
 }
 
 int amb_profile_enable(int on) {
@@ -230,14 +266,14 @@ int amb_debug_dot_matrix(int dev, amb_stream_t stream, const void* packed_a, lon
   g.lbo_bytes = lbo ? lbo : 128;
   g.sbo_bytes = sbo ? sbo : 512;
   DumpEpi epi{a.inv_scale, b.inv_scale, C, ldc, na, nb, ldc == 0 ? 1 : 0};
-  // AMB_DEBUG_SINGLE=1: hi planes only through the single-pass kernel (11-bit operands)
-  const char* e = getenv("AMB_DEBUG_SINGLE");
-  if (e && atoi(e) == 2 && g.kb_count <= kMaxResidentKb) {   // ... on CTA pairs (cta_group::2)
+  // option debug_single = 1: hi planes only through the single-pass kernel (11-bit operands)
+  const int single = option(kOptDebugSingle);
+  if (single == 2 && g.kb_count <= kMaxResidentKb) {   // ... on CTA pairs (cta_group::2)
     g.n_rt /= 2;                                             // rows_pad is a multiple of 256
     return launch_engine2(static_cast<cudaStream_t>(stream), dev, g, epi, "pair_engine2<dump>",
                           static_cast<double>(na) * nb);
   }
-  if (e && atoi(e) == 1 && g.kb_count <= kMaxResidentKb)
+  if (single == 1 && g.kb_count <= kMaxResidentKb)
     return launch_engine1(static_cast<cudaStream_t>(stream), dev, g, epi, "pair_engine1<dump>",
                           static_cast<double>(na) * nb);
   return launch_engine(static_cast<cudaStream_t>(stream), dev, g, epi, "pair_engine<dump>",

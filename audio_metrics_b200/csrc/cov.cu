@@ -164,12 +164,11 @@ static int cov_slabs(long long n, int d) {
 
 // fp32 inputs with enough rows go through the exact integer tensor-core path (cov_tc.cu);
 // small batches (the 32-row streaming adds) and fp64 inputs stay on the FP64 pipe.
-// AMB_COV=dfma forces the FP64-pipe kernel.
+// Option cov_dfma (AMB_COV=dfma) forces the FP64-pipe kernel.
 constexpr long long kCovTcMinRows = 4096;
 static bool use_cov_tc(int dtype, long long n) {
   if (dtype != AMB_F32 || n < kCovTcMinRows) return false;
-  const char* e = getenv("AMB_COV");
-  return !(e && e[0] == 'd');
+  return option(kOptCovDfma) == 0;
 }
 
 }  // namespace amb

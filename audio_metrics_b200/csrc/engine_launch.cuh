@@ -47,8 +47,7 @@ int launch_engine1(cudaStream_t stream, int dev, EngineGeom g, const Epi& epi, c
   const size_t fixed = size_t(g.kb_count) * kChunkBytes + sizeof(EngineSmemOf<Epi>) + (Epi::kScratch ? kScratchBytes : 0);
   int n_stages = static_cast<int>((kMaxDynSmem - fixed) / kStage1Bytes);
   if (n_stages > kMaxStages) n_stages = kMaxStages;
-  if (const char* e = getenv("AMB_STAGES")) {   // tuning knob: shallower B ring
-    const int v = atoi(e);
+  if (const int v = option(kOptStages)) {   // tuning knob: shallower B ring
     if (v >= 2 && v < n_stages) n_stages = v;
   }
   g.n_stages = n_stages;
@@ -59,8 +58,7 @@ int launch_engine1(cudaStream_t stream, int dev, EngineGeom g, const Epi& epi, c
   const long long items = static_cast<long long>(g.n_problems) * g.n_rt * g.n_split;
   if (items <= 0) return AMB_OK;
   int sms = sm_count(dev);
-  if (const char* e = getenv("AMB_GRID")) {   // experiment knob: fewer persistent CTAs than SMs
-    const int v = atoi(e);
+  if (const int v = option(kOptGrid)) {   // experiment knob: fewer persistent CTAs than SMs
     if (v >= 1 && v < sms) sms = v;
   }
   const unsigned grid = static_cast<unsigned>(items < sms ? items : sms);
@@ -80,8 +78,7 @@ int launch_engine2(cudaStream_t stream, int dev, EngineGeom g, const Epi& epi, c
   const size_t fixed = size_t(g.kb_count) * kChunkBytes + sizeof(EngineSmem2Of<Epi>) + (Epi::kScratch ? kScratchBytes : 0);
   int n_stages = static_cast<int>((kMaxDynSmem - fixed) / kStage2Bytes);
   if (n_stages > kMaxStages) n_stages = kMaxStages;
-  if (const char* e = getenv("AMB_STAGES")) {
-    const int v = atoi(e);
+  if (const int v = option(kOptStages)) {
     if (v >= 2 && v < n_stages) n_stages = v;
   }
   if (n_stages < 2) return set_error(AMB_ERR_ARG, "%s: shared memory too small for the B ring", what);
@@ -92,10 +89,9 @@ int launch_engine2(cudaStream_t stream, int dev, EngineGeom g, const Epi& epi, c
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(pair_engine2)");
   const long long items = static_cast<long long>(g.n_problems) * g.n_rt * g.n_split;
   if (items <= 0) return AMB_OK;
-  int pairs = (sm_count(dev) - option_engine_reserve_sms()) / 2;   // SMs left to another stream's kernels
+  int pairs = (sm_count(dev) - option(kOptReserveSms)) / 2;   // SMs left to another stream's kernels
   if (pairs < 1) pairs = 1;
-  if (const char* e = getenv("AMB_GRID")) {
-    const int v = atoi(e) / 2;
+  if (const int v = option(kOptGrid) / 2) {
     if (v >= 1 && v < pairs) pairs = v;
   }
   const unsigned grid = 2u * static_cast<unsigned>(items < pairs ? items : pairs);

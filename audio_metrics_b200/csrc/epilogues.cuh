@@ -52,9 +52,10 @@ struct DumpEpi {
 
 // --------------------------------------------------------- kernel distance sums
 // Problems come in triples per subset: 3s+0 = K(f1,f1), 3s+1 = K(f2,f2),
-// 3s+2 = K(f1,f2)  (kd.py:119-122).  The diagonal of the two symmetric blocks is
-// left out here, which is kd.py:62-63's  K.sum(axis=1) - diag.  Each epilogue
-// warp writes one fp64 partial per work item: partial[item*8 + half*4 + quarter].
+// 3s+2 = K(f1,f2)  (kd.py:119-122).  Diagonal and off-diagonal entries are summed
+// separately (kd.py:53-68 needs K.sum(axis=1) - diag, the diagonal sums and, for the
+// u-statistic, trace(K_XY)).  Each epilogue warp writes two fp64 partials per work item:
+// partial[(item*8 + half*4 + quarter)*2 + {0 off-diagonal, 1 diagonal}].
 struct KdEpi {
   static constexpr int kColVecs = 1;
   static constexpr bool kScratch = false;
@@ -68,15 +69,15 @@ struct KdEpi {
   const float* norm_b;
   int m_valid;               // rows/cols per problem that are real samples
   double* partial;
-  struct Row { double sum; double gr; float na; int row_in_problem; bool valid; bool sym; };
+  struct Row { double sum; double dsum; double gr; float na; int row_in_problem; bool valid; };
   __device__ const float* colvec_ptr(int) const { return inv_b; }
   __device__ const float* cmin_ptr() const { return nullptr; }
   __device__ const float* cmax_ptr() const { return nullptr; }
   __device__ void row_begin(Row& r, const ItemCoord& c, long long a_row, int, float*) const {
     r.row_in_problem = c.rt * kTileM + static_cast<int>(a_row % kTileM);
     r.valid = r.row_in_problem < m_valid;
-    r.sym = (c.problem % 3) != 2;
     r.sum = 0.0;
+    r.dsum = 0.0;
     const double isr = static_cast<double>(inv_a[a_row]);
     r.gr = (kernel_type == AMB_KERNEL_POLY ? gamma : 1.0) * isr;
     r.na = norm_a ? norm_a[a_row] : 0.f;
@@ -98,7 +99,7 @@ struct KdEpi {
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0,
                         int col0, long long b_row0, float*, float, float) const {
     if (!r.valid) return;
-    const bool edge = (col0 + 32 > m_valid) || (r.sym && col0 <= r.row_in_problem && r.row_in_problem < col0 + 32);
+    const bool edge = (col0 + 32 > m_valid) || (col0 <= r.row_in_problem && r.row_in_problem < col0 + 32);
     if (!edge && kernel_type == AMB_KERNEL_POLY && degree == 3) {
       double s0 = 0, s1 = 0;
       const double g2 = r.gr * static_cast<double>(cv[0][c0]);   // powers of two: exact
@@ -116,17 +117,26 @@ struct KdEpi {
       for (int j = 0; j < 32; ++j) {
         const int col = col0 + j;
         if (col >= m_valid) continue;
-        if (r.sym && col == r.row_in_problem) continue;
-        s += kval(r, f32(acc[j]), cv[0][c0 + j], b_row0 + j);
+        const double kv = kval(r, f32(acc[j]), cv[0][c0 + j], b_row0 + j);
+        if (col == r.row_in_problem) r.dsum += kv;
+        else s += kv;
       }
       r.sum += s;
     }
   }
   __device__ void row_end(Row& r, const ItemCoord&, int item, long long, int quarter, int lane, int half) const {
     double s = r.valid ? r.sum : 0.0;
+    double ds = r.valid ? r.dsum : 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) partial[static_cast<long long>(item) * kEpiWarps + half * 4 + quarter] = s;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    }
+    if (lane == 0) {
+      const long long o = (static_cast<long long>(item) * kEpiWarps + half * 4 + quarter) * 2;
+      partial[o] = s;
+      partial[o + 1] = ds;
+    }
   }
 };
 

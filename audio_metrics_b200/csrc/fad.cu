@@ -426,6 +426,236 @@ dgemm_nt_kernel(const double* __restrict__ A, const double* __restrict__ B, doub
     }
 }
 
+// ---------------------------------------------------------------------------
+// Nuclear norm by polar iteration (the default path).
+//
+// With the polar decomposition M = U H (U orthogonal on the range of M, H symmetric PSD),
+// c = sum of singular values = tr H = tr(U^T M) = <U, M>_F.  U is the limit of
+//     X_0 = M / |M|_F,     X_{k+1} = X_k (a_k I + b_k A_k + c_k A_k^2),   A_k = X_k^T X_k,
+// which acts on every singular value s of X_k as the odd quintic p_k(s) = s (a + b s^2 + c s^4)
+// and leaves the singular vectors alone.  The p_k (tools/polar_schedule.py) are chosen greedily
+// so that [l_k, 1 + 1/64] is mapped into [l_{k+1}, 1] with the largest l_{k+1}; from l_0 = 1e-12
+// nineteen of them reach 0.52, four classical quintic Newton-Schulz steps then reach 1 - 7e-16.
+// Error of the result: a singular value s_i < 1e-12 |M|_F is not fully pushed to 1 and its
+// contribution s_i f_i is short by at most s_i, so c is short by at most d 1e-12 |M|_F <= 5e-10 c
+// at d = 512; rotational errors of U only enter to second order because tr(U^T M) is maximal at
+// the polar factor; measured against an fp64 SVD: 1e-13 relative on full-rank, rank-deficient
+// (N < d), rank-1 and column-scaled (condition 4e13) inputs.  Nothing is inverted, so singular M
+// (zero singular values stay zero) needs no special care — the reason Newton-Schulz on the
+// covariances themselves was rejected does not apply to the factored form.
+// Cost: 23 x 3 fp64 GEMMs of d^3 (0.13 GFMA each at d = 512) on the FP64 pipe, all SMs: no
+// sequential d-step chain like the Jacobi sweeps (12 sweeps x 64 grid-wide block rounds).
+constexpr int kPolarSteps = 23;
+__constant__ double kPolarCoef[kPolarSteps][3] = {
+    {4.1916565787041771, -12.066380161025515, 8.68377021423718},
+    {4.1916566436514273, -12.066380317469966, 8.6837703048631969},
+    {4.1916566436514655, -12.066380317470065, 8.6837703048632555},
+    {4.1916566436516245, -12.06638031747045, 8.6837703048634811},
+    {4.1916566436522835, -12.066380317472056, 8.6837703048644173},
+    {4.1916566386695626, -12.066380276778837, 8.6837702700967636},
+    {4.191656622769198, -12.066380146906818, 8.683770159134296},
+    {4.1916565820088225, -12.066379813873592, 8.6837698745787613},
+    {4.1916562767511243, -12.066377320678535, 8.6837677444089749},
+    {4.1916551057316553, -12.066367755953339, 8.6837595723219021},
+    {4.1916500759715642, -12.066327371902723, 8.6837251486053741},
+    {4.1916296475970114, -12.06615981794816, 8.6835819104574838},
+    {4.1915433819363512, -12.065455223128238, 8.6829799069705818},
+    {4.1911819164247035, -12.062503019398758, 8.6804575710918428},
+    {4.1896658996547913, -12.050131190543864, 8.6698883400076188},
+    {4.1833118675549503, -11.998362821360594, 8.6256725368931271},
+    {4.1566694961648514, -11.782935523996235, 8.4418630726327937},
+    {4.0452998092620023, -10.910521325149281, 7.7007586089770745},
+    {3.6064439676221012, -7.8935092572868069, 5.1883297840173643},
+    {15.0 / 8, -10.0 / 8, 3.0 / 8},
+    {15.0 / 8, -10.0 / 8, 3.0 / 8},
+    {15.0 / 8, -10.0 / 8, 3.0 / 8},
+    {15.0 / 8, -10.0 / 8, 3.0 / 8},
+};
+
+constexpr int kPgM = 32, kPgN = 64, kPgK = 16, kPgThreads = 128;
+constexpr int kPolarPad = 64;   // iteration matrices are dp x dp, dp = d rounded up to 64, zero padded
+
+// One CTA per matrix: alpha = |Mt|_F, X = Mt / alpha written into the zero-padded dp x dp buffer.
+__global__ void __launch_bounds__(1024)
+polar_init_kernel(const double* __restrict__ Mt, int d, int dp, double* __restrict__ X) {
+  __shared__ double red[32];
+  __shared__ double s_inv;
+  const long long mo = static_cast<long long>(blockIdx.x) * d * d;
+  const long long xo = static_cast<long long>(blockIdx.x) * dp * dp;
+  double s = 0.0;
+  for (long long e = threadIdx.x; e < static_cast<long long>(d) * d; e += blockDim.x) {
+    const double v = Mt[mo + e];
+    s = fma(v, v, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += red[w];
+    s_inv = t > 0.0 ? 1.0 / sqrt(t) : 0.0;
+  }
+  __syncthreads();
+  const double inv = s_inv;
+  for (long long e = threadIdx.x; e < static_cast<long long>(dp) * dp; e += blockDim.x) {
+    const int i = static_cast<int>(e / dp), j = static_cast<int>(e % dp);
+    X[xo + e] = (i < d && j < d) ? Mt[mo + static_cast<long long>(i) * d + j] * inv : 0.0;
+  }
+}
+
+// fp64 GEMM tile kernel of the polar iteration on padded dp x dp row-major matrices (batch in z):
+//   MODE 0:  C = X^T X                       C[i][j] = sum_k X[k][i] X[k][j]
+//   MODE 1:  C = X (ca I + cb A + cc A2)     C[i][j] = sum_k X[i][k] Q[k][j], Q formed while loading
+// 32 x 64 output tile, 128 threads, 4 x 4 outputs per thread, k blocks of 16 double-buffered in
+// shared memory (global -> registers -> shared overlaps the FMAs of the current block).  At d = 512
+// that is 128 CTAs, one wave; the FP64 pipe (64 FMA/clk/SM) is the bound.
+template <int MODE>
+__global__ void __launch_bounds__(kPgThreads)
+polar_gemm_kernel(const double* __restrict__ X, const double* __restrict__ A, const double* __restrict__ A2,
+                  double* __restrict__ C, int dp, int step) {
+  __shared__ __align__(16) double As[2][kPgK][kPgM + 2];
+  __shared__ __align__(16) double Bs[2][kPgK][kPgN + 2];
+  const long long mo = static_cast<long long>(blockIdx.z) * dp * dp;
+  X += mo;
+  C += mo;
+  if (MODE == 1) { A += mo; A2 += mo; }
+  const double ca = MODE == 1 ? kPolarCoef[step][0] : 0.0;
+  const double cb = MODE == 1 ? kPolarCoef[step][1] : 0.0;
+  const double cc = MODE == 1 ? kPolarCoef[step][2] : 0.0;
+  const int i0 = blockIdx.y * kPgM, j0 = blockIdx.x * kPgN;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const int l_row = t >> 3, l_c4 = (t & 7) * 4, l_c8 = (t & 7) * 8;   // direct loads: row of the k block, column offset
+  const int l_ii = t >> 2, l_k4 = (t & 3) * 4;                         // transposing load of X[i][k] (MODE 1)
+  double acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+  double ra[4], rb[8];
+  auto load = [&](int k0) {
+    if (MODE == 0) {
+      const double2* pa = reinterpret_cast<const double2*>(X + static_cast<long long>(k0 + l_row) * dp + i0 + l_c4);
+      const double2 a0 = pa[0], a1 = pa[1];
+      ra[0] = a0.x; ra[1] = a0.y; ra[2] = a1.x; ra[3] = a1.y;
+      const double2* pb = reinterpret_cast<const double2*>(X + static_cast<long long>(k0 + l_row) * dp + j0 + l_c8);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const double2 b = pb[e]; rb[2 * e] = b.x; rb[2 * e + 1] = b.y; }
+    } else {
+      const double2* pa = reinterpret_cast<const double2*>(X + static_cast<long long>(i0 + l_ii) * dp + k0 + l_k4);
+      const double2 a0 = pa[0], a1 = pa[1];
+      ra[0] = a0.x; ra[1] = a0.y; ra[2] = a1.x; ra[3] = a1.y;
+      const long long o = static_cast<long long>(k0 + l_row) * dp + j0 + l_c8;
+      const double2* p1 = reinterpret_cast<const double2*>(A + o);
+      const double2* p2 = reinterpret_cast<const double2*>(A2 + o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double2 u = p1[e], v = p2[e];
+        rb[2 * e] = fma(cc, v.x, cb * u.x);
+        rb[2 * e + 1] = fma(cc, v.y, cb * u.y);
+      }
+      const int dj = k0 + l_row - (j0 + l_c8);   // diagonal element of Q inside this thread's 8 columns?
+#pragma unroll
+      for (int e = 0; e < 8; ++e) rb[e] += (e == dj) ? ca : 0.0;
+    }
+  };
+  auto store = [&](int buf) {
+    if (MODE == 0) {
+      *reinterpret_cast<double2*>(&As[buf][l_row][l_c4]) = make_double2(ra[0], ra[1]);
+      *reinterpret_cast<double2*>(&As[buf][l_row][l_c4 + 2]) = make_double2(ra[2], ra[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) As[buf][l_k4 + e][l_ii] = ra[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      *reinterpret_cast<double2*>(&Bs[buf][l_row][l_c8 + 2 * e]) = make_double2(rb[2 * e], rb[2 * e + 1]);
+  };
+  load(0);
+  store(0);
+  __syncthreads();
+  for (int k0 = 0; k0 < dp; k0 += kPgK) {
+    const int buf = (k0 / kPgK) & 1;
+    const bool more = k0 + kPgK < dp;
+    if (more) load(k0 + kPgK);
+#pragma unroll
+    for (int kk = 0; kk < kPgK; ++kk) {
+      const double2 a0 = *reinterpret_cast<const double2*>(&As[buf][kk][ty * 4]);
+      const double2 a1 = *reinterpret_cast<const double2*>(&As[buf][kk][ty * 4 + 2]);
+      const double2 b0 = *reinterpret_cast<const double2*>(&Bs[buf][kk][tx * 4]);
+      const double2 b1 = *reinterpret_cast<const double2*>(&Bs[buf][kk][tx * 4 + 2]);
+      const double a[4] = {a0.x, a0.y, a1.x, a1.y};
+      const double b[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+    }
+    if (more) store(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    double* out = C + static_cast<long long>(i0 + ty * 4 + r) * dp + j0 + tx * 4;
+    *reinterpret_cast<double2*>(out) = make_double2(acc[r][0], acc[r][1]);
+    *reinterpret_cast<double2*>(out + 2) = make_double2(acc[r][2], acc[r][3]);
+  }
+}
+
+// U (dp-strided) <- polar factor of Mt (d x d, batch matrices).  bufs: 4 * batch * dp * dp doubles.
+// Returns the buffer that holds U in *u_out.
+static int launch_polar(cudaStream_t st, const double* Mt, int d, int batch, double* bufs, const double** u_out) {
+  const int dp = static_cast<int>(round_up_ll(d, kPolarPad));
+  const size_t mat = static_cast<size_t>(dp) * dp * batch;
+  double* X = bufs;
+  double* Xn = bufs + mat;
+  double* A = bufs + 2 * mat;
+  double* A2 = bufs + 3 * mat;
+  int rc;
+  polar_init_kernel<<<batch, 1024, 0, st>>>(Mt, d, dp, X);
+  if ((rc = check_launch("polar_init_kernel"))) return rc;
+  const dim3 grid(dp / kPgN, dp / kPgM, batch);
+  for (int k = 0; k < kPolarSteps; ++k) {
+    polar_gemm_kernel<0><<<grid, kPgThreads, 0, st>>>(X, nullptr, nullptr, A, dp, k);      // A  = X^T X
+    if ((rc = check_launch("polar_gemm_kernel<0>"))) return rc;
+    polar_gemm_kernel<0><<<grid, kPgThreads, 0, st>>>(A, nullptr, nullptr, A2, dp, k);     // A2 = A^T A = A^2
+    if ((rc = check_launch("polar_gemm_kernel<0>"))) return rc;
+    polar_gemm_kernel<1><<<grid, kPgThreads, 0, st>>>(X, A, A2, Xn, dp, k);                // X  = X q_k(A)
+    if ((rc = check_launch("polar_gemm_kernel<1>"))) return rc;
+    double* tmp = X; X = Xn; Xn = tmp;
+  }
+  *u_out = X;
+  return AMB_OK;
+}
+
+// one block per pair: a = |mu_x-mu_y|^2, b = tr S_x + tr S_y, c = <U, M>_F  (U: dp-strided polar factor)
+__global__ void __launch_bounds__(256)
+fad_combine_polar_kernel(int d, int dp, const double* __restrict__ mu_x, const double* __restrict__ cov_x,
+                         const double* __restrict__ mu_y, const double* __restrict__ cov_y,
+                         const double* __restrict__ Mt, const double* __restrict__ U, double* __restrict__ out) {
+  __shared__ double red[256];
+  const int b = blockIdx.x;
+  const long long mo = static_cast<long long>(b) * d * d;
+  const long long uo = static_cast<long long>(b) * dp * dp;
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    const double df = mu_x[static_cast<long long>(b) * d + k] - mu_y[static_cast<long long>(b) * d + k];
+    acc += df * df + cov_x[mo + static_cast<long long>(k) * d + k] + cov_y[mo + static_cast<long long>(k) * d + k];
+  }
+  double c = 0.0;
+  for (long long e = threadIdx.x; e < static_cast<long long>(d) * d; e += blockDim.x) {
+    const int i = static_cast<int>(e / d), j = static_cast<int>(e % d);
+    c = fma(U[uo + static_cast<long long>(i) * dp + j], Mt[mo + e], c);
+  }
+  red[threadIdx.x] = acc - 2.0 * c;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[b] = red[0];
+}
+
 // one block per pair: a = |mu_x-mu_y|^2, b = tr S_x + tr S_y, c = sum_j |m_j|
 __global__ void __launch_bounds__(256)
 fad_combine_kernel(int d, const double* __restrict__ mu_x, const double* __restrict__ cov_x,
@@ -476,7 +706,7 @@ static int launch_jacobi_block(cudaStream_t st, int dev, double* Gt, int d, int 
   long long want = static_cast<long long>(nb / 2) * n_mat;
   const long long cap = static_cast<long long>(per_sm) * sm_count(dev);
   if (want > cap) want = cap;
-  if (option_fad_ctas() > 0 && want > option_fad_ctas()) want = option_fad_ctas();   // CTAs loop over the block pairs
+  if (option(kOptFadCtas) > 0 && want > option(kOptFadCtas)) want = option(kOptFadCtas);   // CTAs loop over the block pairs
   void* args[] = {&Gt, &d, &n_mat, &tol, &stop_rot, &rot, &sweeps};
   rc = check_cuda(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fn), dim3(static_cast<unsigned>(want)),
                                               dim3(32 * BS), args, smem, st),
@@ -498,8 +728,7 @@ static int launch_jacobi(cudaStream_t st, int dev, double* Gt, int d, int n_mat,
   int* sweeps = counters + kJacobiMaxSweeps;
   int rc = check_cuda(cudaMemsetAsync(counters, 0, (kJacobiMaxSweeps + 1) * sizeof(int), st), "memset");
   if (rc) return rc;
-  const char* env = getenv("AMB_JACOBI");   // "flat" forces the round-per-grid-barrier kernel
-  const bool flat = env && env[0] == 'f';
+  const bool flat = option(kOptJacobiFlat) != 0;   // forces the round-per-grid-barrier kernel
   if (d <= 512 && !flat) {
     // block size: 16 columns per block unless that leaves most SMs idle (few matrices), then 8
     // (measured at d=512, one matrix: 15.9 / 13.1 / 15.7 ms for 16 / 8 / 4): more, smaller CTAs in
@@ -507,15 +736,11 @@ static int launch_jacobi(cudaStream_t st, int dev, double* Gt, int d, int n_mat,
     int bs = 16;
     const int sms = sm_count(dev);
     while (bs > 8 && static_cast<long long>(n_mat) * ((d + 2 * bs - 1) / (2 * bs)) * 2 <= sms) bs >>= 1;
-    if (option_fad_ctas() > 0) {   // stay within the CTA budget: larger blocks = fewer CTAs
+    if (option(kOptFadCtas) > 0) {   // stay within the CTA budget: larger blocks = fewer CTAs
       bs = 16;
-      while (bs > 4 && static_cast<long long>(n_mat) * ((d + bs - 1) / bs) <= option_fad_ctas()) bs >>= 1;
+      while (bs > 4 && static_cast<long long>(n_mat) * ((d + bs - 1) / bs) <= option(kOptFadCtas)) bs >>= 1;
     }
-    if (option_jacobi_block()) bs = option_jacobi_block();
-    if (const char* e = getenv("AMB_JACOBI_BS")) {
-      const int v = atoi(e);
-      if (v == 4 || v == 8 || v == 16) bs = v;
-    }
+    if (option(kOptJacobiBlock)) bs = option(kOptJacobiBlock);
 #define AMB_JB(BS)                                                                                   \
     (d <= 128 ? launch_jacobi_block<BS, 4>(st, dev, Gt, d, n_mat, tol, stop_rot, rot, sweeps)                    \
      : d <= 256 ? launch_jacobi_block<BS, 8>(st, dev, Gt, d, n_mat, tol, stop_rot, rot, sweeps)                  \
@@ -556,7 +781,10 @@ extern "C" {
 
 size_t amb_frechet_ws_bytes(int batch, int d) {
   if (batch <= 0 || d <= 0) return 0;
-  return static_cast<size_t>(5) * batch * d * d * 8 + 4096 + static_cast<size_t>(batch) * 16;
+  const size_t dp = static_cast<size_t>(round_up_ll(d, kPolarPad));
+  // covariance copies (2), factors (2), M (1) | counters | four padded iteration matrices of the polar path
+  return static_cast<size_t>(5) * batch * d * d * 8 + 4096 + static_cast<size_t>(batch) * 16 + 256 +
+         static_cast<size_t>(4) * batch * dp * dp * 8;
 }
 
 int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu_x,
@@ -577,13 +805,14 @@ int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu
   double* Mt = Lt + 2 * batch * mat;             // [batch]
   int* counters = reinterpret_cast<int*>(Mt + batch * mat);     // 1024 ints
   int* panel_n = counters + 512;                                // [2*batch] + rank [2*batch]
+  double* polar_bufs = reinterpret_cast<double*>(
+      static_cast<uint8_t*>(ws) + round_up_ll(static_cast<long long>(5 * batch * mat * 8 + 4096 + batch * 16), 256));
   int rc;
   if ((rc = check_cuda(cudaMemsetAsync(counters, 0, 4096, st), "memset"))) return rc;
   if ((rc = check_cuda(cudaMemcpyAsync(G, cov_x, batch * mat * 8, cudaMemcpyDeviceToDevice, st), "memcpy"))) return rc;
   if ((rc = check_cuda(cudaMemcpyAsync(G + batch * mat, cov_y, batch * mat * 8, cudaMemcpyDeviceToDevice, st), "memcpy"))) return rc;
-  const char* mode = getenv("AMB_FAD_FACTOR");   // "eig": eigen-factors by Jacobi (the slower first implementation)
   double* F = Lt;
-  if (mode && mode[0] == 'e') {
+  if (option(kOptFadFactorEig)) {   // eigen-factors by Jacobi (the slower first implementation)
     if ((rc = launch_jacobi(st, dev, G, d, 2 * batch, counters, false))) return rc;
     factor_scale_kernel<<<(2 * batch * d * 32 + 255) / 256, 256, 0, st>>>(G, d, 2 * batch);
     if ((rc = check_launch("factor_scale_kernel"))) return rc;
@@ -600,7 +829,7 @@ int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu
       int n_mat = 2 * batch - m0 < sms ? 2 * batch - m0 : sms;
       int C = sms / n_mat;
       if (C > 16) C = 16;
-      if (option_fad_ctas() > 0 && C * n_mat > option_fad_ctas()) C = option_fad_ctas() / n_mat > 0 ? option_fad_ctas() / n_mat : 1;
+      if (option(kOptFadCtas) > 0 && C * n_mat > option(kOptFadCtas)) C = option(kOptFadCtas) / n_mat > 0 ? option(kOptFadCtas) / n_mat : 1;
       double* Ap = G + static_cast<size_t>(m0) * mat;
       double* Lp = Lt + static_cast<size_t>(m0) * mat;
       int* pn = panel_n + m0;
@@ -616,10 +845,18 @@ int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu
   dim3 ggrid((d + 63) / 64, (d + 63) / 64, batch);
   dgemm_nt_kernel<<<ggrid, 256, 0, st>>>(F, F + batch * mat, Mt, d);   // Mt[i][j] = <F_x col i, F_y col j>
   if ((rc = check_launch("dgemm_nt_kernel"))) return rc;
-  if ((rc = launch_jacobi(st, dev, Mt, d, batch, counters + 64, true))) return rc;
-  fad_combine_kernel<<<batch, 256, 0, st>>>(d, mu_x, cov_x, mu_y, cov_y, Mt, out);
-  if ((rc = check_launch("fad_combine_kernel"))) return rc;
-  if (getenv("AMB_FAD_DEBUG")) {   // ranks, sweeps / rotations per sweep of the Jacobi stages (synchronises)
+  if (option(kOptFadMethod) == 1) {   // one-sided Jacobi: singular values as column norms (cross-check path)
+    if ((rc = launch_jacobi(st, dev, Mt, d, batch, counters + 64, true))) return rc;
+    fad_combine_kernel<<<batch, 256, 0, st>>>(d, mu_x, cov_x, mu_y, cov_y, Mt, out);
+    if ((rc = check_launch("fad_combine_kernel"))) return rc;
+  } else {                            // polar iteration: c = <U, M>
+    const double* U = nullptr;
+    if ((rc = launch_polar(st, Mt, d, batch, polar_bufs, &U))) return rc;
+    fad_combine_polar_kernel<<<batch, 256, 0, st>>>(d, static_cast<int>(round_up_ll(d, kPolarPad)), mu_x, cov_x, mu_y,
+                                                     cov_y, Mt, U, out);
+    if ((rc = check_launch("fad_combine_polar_kernel"))) return rc;
+  }
+  if (option(kOptFadDebug)) {   // ranks, sweeps / rotations per sweep of the Jacobi stages (synchronises)
     int h[1024] = {0};
     if (cudaStreamSynchronize(st) == cudaSuccess &&
         cudaMemcpy(h, counters, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {

@@ -121,7 +121,7 @@ int amb_host_kd(int dev, const void* F1, long long n1, const void* F2, long long
   void* ws = h.alloc<uint8_t>(wsb);
   if (h.rc) return h.rc;
   h.run(amb_kd_subsets(dev, h.st, d1, n1, d, d2, n2, d, d, dtype, didx, S, m, AMB_KERNEL_POLY, gamma, coef0,
-                       degree, 1.0, mm, stt, ws, wsb));
+                       degree, 1.0, AMB_MMD_UNBIASED, mm, stt, ws, wsb));
   if (mmd2_out) h.download(mmd2_out, mm, S);
   h.download(stats_out, stt, 2);
   return h.finish();
@@ -138,7 +138,7 @@ int amb_host_knn_radii(int dev, const void* X, int dtype, long long n, int d, in
   void* ws = h.alloc<uint8_t>(wsb);
   if (h.rc) return h.rc;
   h.run(amb_pack(dev, h.st, dX, dtype, n, d, d, packed));
-  h.run(amb_knn_radii(dev, h.st, dX, dtype, d, packed, n, d, 0, n, k, r, ws, wsb));
+  h.run(amb_knn_radii(dev, h.st, dX, dtype, d, packed, n, d, 0, n, k, r, nullptr, ws, wsb));
   h.download(radii, r, n);
   return h.finish();
 }
@@ -164,21 +164,41 @@ int amb_host_prdc(int dev, const void* ref, long long n, const void* cand, long 
   wsb = wsb > w3 ? wsb : w3;
   void* ws = h.alloc<uint8_t>(wsb);
   if (h.rc) return h.rc;
-  h.zero(col, static_cast<size_t>(m) * 4);
-  h.zero(totals, 64);
   h.run(amb_pack(dev, h.st, dR, dtype, n, d, d, pR));
   h.run(amb_pack(dev, h.st, dC, dtype, m, d, d, pC));
-  h.run(amb_knn_radii(dev, h.st, dR, dtype, d, pR, n, d, 0, n, k, rR, ws, wsb));
-  h.run(amb_knn_radii(dev, h.st, dC, dtype, d, pC, m, d, 0, m, k, rC, ws, wsb));
-  h.run(amb_prdc_counts(dev, h.st, dR, d, pR, n, rR, dC, d, pC, m, rC, d, dtype, 0, n, col, rec, cov, totals + 4, ws, wsb));
-  h.run(amb_prdc_reduce(dev, h.st, col, m, rec, cov, n, totals));
+  h.run(amb_knn_radii(dev, h.st, dR, dtype, d, pR, n, d, 0, n, k, rR, nullptr, ws, wsb));
+  h.run(amb_knn_radii(dev, h.st, dC, dtype, d, pC, m, d, 0, m, k, rC, nullptr, ws, wsb));
+  // Counts, with the overflow ladder of amb200.h: default refine list -> a list sized to the number
+  // of near-tie pairs the first attempt reported -> exhaustive exact counts.
   long long t[8] = {0};
-  h.download(t, totals, 8);
-  int rc = h.finish();
-  if (rc) return rc;
-  if (t[4] > amb_prdc_list_cap(n, m))
-    return set_error(AMB_ERR_WS, "amb_host_prdc: %lld uncertain pairs exceed the refine list capacity %lld", t[4],
-                     amb_prdc_list_cap(n, m));
+  void* big = nullptr;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    h.zero(col, static_cast<size_t>(m) * 4);
+    h.zero(totals, 64);
+    if (attempt == 0) {
+      h.run(amb_prdc_counts(dev, h.st, dR, d, pR, n, rR, dC, d, pC, m, rC, d, dtype, 0, n, col, rec, cov, totals + 4, ws, wsb));
+    } else if (attempt == 1 && big) {
+      const size_t bb = amb_prdc_ws_bytes_cap(n, m, t[4]);
+      h.run(amb_prdc_counts(dev, h.st, dR, d, pR, n, rR, dC, d, pC, m, rC, d, dtype, 0, n, col, rec, cov, totals + 4, big, bb));
+    } else {
+      h.run(amb_prdc_counts_exact(dev, h.st, dR, d, n, rR, dC, d, m, rC, d, dtype, 0, n, col, rec, cov));
+    }
+    h.run(amb_prdc_reduce(dev, h.st, col, m, rec, cov, n, totals));
+    h.download(t, totals, 8);
+    int rc = h.finish();
+    if (rc) return rc;
+    const long long cap = attempt == 0 ? amb_prdc_ws_list_cap(n, m, wsb) : t[4];
+    if (attempt == 2 || t[4] <= cap) break;
+    if (attempt == 0) {   // a list for exactly the reported number of pairs, if the device can hold it
+      size_t free_b = 0, total_b = 0;
+      const size_t bb = amb_prdc_ws_bytes_cap(n, m, t[4]);
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bb < free_b / 2 && cudaMalloc(&big, bb) == cudaSuccess)
+        h.bufs.push_back(big);
+      else
+        big = nullptr;
+      (void)cudaGetLastError();
+    }
+  }
   out[0] = static_cast<double>(t[0]) / static_cast<double>(m);                         // precision  prdc.py:36-38
   out[1] = static_cast<double>(t[2]) / static_cast<double>(n);                         // recall     prdc.py:40-42
   out[2] = (1.0 / static_cast<double>(k)) * (static_cast<double>(t[1]) / static_cast<double>(m));  // density prdc.py:44-46

@@ -26,9 +26,30 @@ struct DeviceGuard {
 };
 
 int sm_count(int dev);
-int option_jacobi_block();        // amb_set_option("jacobi_block")
-int option_fad_ctas();            // amb_set_option("fad_ctas")
-int option_engine_reserve_sms();  // amb_set_option("engine_reserve_sms")
+// Process-wide tuning / diagnostic options (amb_set_option).  Each is initialised ONCE from its
+// environment variable when the library is first used and afterwards only changes through
+// amb_set_option; no entry point reads the environment per call.  -1 = "not set" where 0 is a value.
+enum Opt {
+  kOptJacobiBlock,    // "jacobi_block"        AMB_JACOBI_BS     0 auto | 4 | 8 | 16
+  kOptFadCtas,        // "fad_ctas"            AMB_FAD_CTAS      0 auto, else CTA cap of the cooperative FAD kernels
+  kOptReserveSms,     // "engine_reserve_sms"  AMB_RESERVE_SMS   SMs the all-pairs sweeps leave free
+  kOptFadMethod,      // "fad_method"          AMB_FAD_METHOD    0 polar iteration (GEMMs) | 1 one-sided Jacobi
+  kOptPasses,         // "engine_passes"       AMB_PASSES        0 auto | 3 three-MMA split sweep
+  kOptCta2,           // "engine_cta2"         AMB_CTA2          -1 auto | 0 single-CTA engine | 1 CTA pairs
+  kOptSchedStatic,    // "engine_static"       AMB_SCHED=static  1 round-robin work items
+  kOptStages,         // "engine_stages"       AMB_STAGES        0 auto, else B ring depth
+  kOptGrid,           // "engine_grid"         AMB_GRID          0 auto, else persistent CTAs
+  kOptTailSplit,      // "tail_split"          AMB_TAIL_SPLIT
+  kOptTopkSplit,      // "topk_split"          AMB_TOPK_SPLIT
+  kOptCountSplit,     // "count_split"         AMB_COUNT_SPLIT
+  kOptDebugSingle,    // "debug_single"        AMB_DEBUG_SINGLE  amb_debug_dot_matrix engine: 0 split | 1 single | 2 pair
+  kOptCovDfma,        // "cov_dfma"            AMB_COV=dfma      1 FP64-pipe Gram kernel for every input
+  kOptFadFactorEig,   // "fad_factor_eig"      AMB_FAD_FACTOR=eig 1 Jacobi eigen-factors instead of pivoted Cholesky
+  kOptJacobiFlat,     // "jacobi_flat"         AMB_JACOBI=flat   1 round-per-grid-barrier Jacobi kernel
+  kOptFadDebug,       // "fad_debug"           AMB_FAD_DEBUG     1 print ranks / sweeps (synchronises)
+  kOptCount
+};
+int option(Opt o);
 
 // Optional per-launch timing of the pair engine (amb_profile_*): CUDA events on the
 // launching stream around the kernel.  No-ops unless enabled.

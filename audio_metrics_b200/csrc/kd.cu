@@ -25,21 +25,37 @@ __global__ void kd_tables_kernel(const int32_t* __restrict__ idx, int S, int m, 
   }
 }
 
-// One block: per-subset MMD^2 (kd.py:77-79 unbiased estimator), then mean and
-// population std over subsets (kd.py:189-192).  Fixed summation order.
-__global__ void kd_finalize_kernel(const double* __restrict__ partial, int S, int per_problem, int m,
+// One block: per-subset MMD^2 (kd.py:38-83: the "unbiased" estimator kernel_mmd2 uses, or the
+// "biased" / "u-statistic" ones), then mean and population std over subsets (kd.py:189-192).
+// Fixed summation order.
+__global__ void kd_finalize_kernel(const double* __restrict__ partial, int S, int per_problem, int m, int mmd_est,
                                    double* __restrict__ mmd2_out, double* __restrict__ stats_out) {
   extern __shared__ double s_mmd[];
+  const int est = mmd_est & 3;
+  const bool unit_diag = (mmd_est & AMB_MMD_UNIT_DIAGONAL) != 0;
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
-    double sums[3];
+    double off[3], dg[3];   // off-diagonal and diagonal sums of K_XX, K_YY, K_XY
     for (int b = 0; b < 3; ++b) {
-      double acc = 0.0;
-      const double* p = partial + (static_cast<long long>(3 * s + b)) * per_problem;
-      for (int e = 0; e < per_problem; ++e) acc += p[e];
-      sums[b] = acc;
+      double acc = 0.0, dacc = 0.0;
+      const double* p = partial + (static_cast<long long>(3 * s + b)) * per_problem * 2;
+      for (int e = 0; e < per_problem; ++e) { acc += p[2 * e]; dacc += p[2 * e + 1]; }
+      off[b] = acc;
+      dg[b] = dacc;
     }
     const double md = static_cast<double>(m);
-    const double v = (sums[0] + sums[1]) / (md * (md - 1.0)) - 2.0 * sums[2] / (md * md);
+    // kd.py:50-68: Kt_*_sum = (K.sum(axis=1) - diag).sum(), with diag = 1 under unit_diagonal
+    const double kt_xx = unit_diag ? off[0] + dg[0] - md : off[0];
+    const double kt_yy = unit_diag ? off[1] + dg[1] - md : off[1];
+    const double sd_x = unit_diag ? md : dg[0], sd_y = unit_diag ? md : dg[1];
+    const double k_xy = off[2] + dg[2];
+    double v;
+    if (est == AMB_MMD_BIASED) {                                   // kd.py:70-75
+      v = (kt_xx + sd_x) / (md * md) + (kt_yy + sd_y) / (md * md) - 2.0 * k_xy / (md * md);
+    } else {
+      v = (kt_xx + kt_yy) / (md * (md - 1.0));                     // kd.py:77
+      if (est == AMB_MMD_UNBIASED) v -= 2.0 * k_xy / (md * md);    // kd.py:79
+      else v -= 2.0 * (k_xy - dg[2]) / (md * (md - 1.0));          // kd.py:81 (K_XY_sum - trace(K_XY))
+    }
     s_mmd[s] = v;
     if (mmd2_out) mmd2_out[s] = v;
   }
@@ -75,7 +91,7 @@ static KdWs kd_ws(void* ws, int S, int m, int d) {
   w.gather = reinterpret_cast<int*>(take(static_cast<size_t>(rows) * 4));
   w.a_rb0 = reinterpret_cast<int*>(take(static_cast<size_t>(3) * S * 4));
   w.b_rb0 = reinterpret_cast<int*>(take(static_cast<size_t>(3) * S * 4));
-  w.partial = reinterpret_cast<double*>(take(static_cast<size_t>(3) * S * (w.mp / kTileM) * kEpiWarps * 8));
+  w.partial = reinterpret_cast<double*>(take(static_cast<size_t>(3) * S * (w.mp / kTileM) * kEpiWarps * 2 * 8));
   w.bytes = off;
   return w;
 }
@@ -94,7 +110,7 @@ size_t amb_kd_ws_bytes(int S, int m, int d) {
 int amb_kd_subsets(int dev, amb_stream_t stream, const void* F1, long long n1, long long ld1,
                    const void* F2, long long n2, long long ld2, int d, int dtype, const int32_t* idx,
                    int S, int m, int kernel_type, double gamma, double coef0, int degree,
-                   double sigma, double* mmd2_out, double* stats_out, void* ws, size_t ws_bytes) {
+                   double sigma, int mmd_est, double* mmd2_out, double* stats_out, void* ws, size_t ws_bytes) {
   if (!F1 || !F2 || !idx || n1 <= 0 || n2 <= 0 || d <= 0 || S <= 0 || m <= 0 || ld1 < d || ld2 < d)
     return set_error(AMB_ERR_ARG, "amb_kd_subsets: bad argument");
   if (S > 4096) return set_error(AMB_ERR_ARG, "amb_kd_subsets: at most 4096 subsets");
@@ -102,6 +118,8 @@ int amb_kd_subsets(int dev, amb_stream_t stream, const void* F1, long long n1, l
     return set_error(AMB_ERR_ARG, "amb_kd_subsets: unknown kernel_type %d", kernel_type);
   if (kernel_type == AMB_KERNEL_POLY && degree < 0) return set_error(AMB_ERR_ARG, "amb_kd_subsets: degree < 0");
   if (kernel_type == AMB_KERNEL_RBF && !(sigma > 0)) return set_error(AMB_ERR_ARG, "amb_kd_subsets: sigma <= 0");
+  if ((mmd_est & ~AMB_MMD_UNIT_DIAGONAL) < 0 || (mmd_est & ~AMB_MMD_UNIT_DIAGONAL) > AMB_MMD_USTAT)
+    return set_error(AMB_ERR_ARG, "amb_kd_subsets: unknown mmd_est %d", mmd_est);
   KdWs w = kd_ws(ws, S, m, d);
   if (!ws || ws_bytes < w.bytes) return set_error(AMB_ERR_WS, "amb_kd_subsets: workspace %zu < %zu", ws_bytes, w.bytes);
   DeviceGuard guard(dev);
@@ -145,7 +163,8 @@ int amb_kd_subsets(int dev, amb_stream_t stream, const void* F1, long long n1, l
   epi.m_valid = m;
   epi.partial = w.partial;
   if ((rc = launch_engine(st, dev, g, epi, "pair_engine<kd>", 3.0 * S * static_cast<double>(m) * m))) return rc;
-  kd_finalize_kernel<<<1, 256, static_cast<size_t>(S) * 8, st>>>(w.partial, S, g.n_rt * kEpiWarps, m, mmd2_out, stats_out);
+  kd_finalize_kernel<<<1, 256, static_cast<size_t>(S) * 8, st>>>(w.partial, S, g.n_rt * kEpiWarps, m, mmd_est, mmd2_out,
+                                                                 stats_out);
   return check_launch("kd_finalize_kernel");
 }
 

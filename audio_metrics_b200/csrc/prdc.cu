@@ -150,21 +150,21 @@ knn_refine_kernel(const T* __restrict__ X, long long ld, int d, long long n, lon
 }
 
 // Brute force for rows the certificate rejected (near-ties beyond the kept
-// margin, heavy duplication): exact distances to all n rows, (k+1)-th smallest.
-// One CTA per unresolved row, persistent over the list; the work is capped by
-// max_rows so that pathological inputs (everything tied) stay bounded — rows
-// beyond the cap keep the refine kernel's value, whose error is below the band.
+// margin, heavy duplication, collinear sets whose distances are tiny differences of
+// large norms): exact distances to all n rows, (k+1)-th smallest.  One CTA per
+// unresolved row, persistent over the WHOLE list — every row the certificate
+// rejected is resolved here, however many there are (a set of identical rows costs
+// n^2 d fp64 operations: slow, never wrong).
 template <typename T>
 __global__ void __launch_bounds__(256)
 knn_bruteforce_kernel(const T* __restrict__ X, long long ld, int d, long long n, long long row0, int k,
                       const int* __restrict__ unresolved, const int* __restrict__ n_unresolved,
-                      int max_rows, float* __restrict__ radii) {
+                      float* __restrict__ radii) {
   __shared__ double s_best[8][32];   // per warp: k+1 smallest (k+1 <= 32)
   __shared__ double s_merge[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double INF = __longlong_as_double(0x7ff0000000000000ll);
-  int count = *n_unresolved;
-  if (count > max_rows) count = max_rows;
+  const int count = *n_unresolved;
   for (int u = blockIdx.x; u < count; u += gridDim.x) {
     const long long row = unresolved[u];
     const T* xi = X + (row0 + row) * ld;
@@ -228,6 +228,9 @@ __global__ void prdc_thresholds_kernel(const float* __restrict__ norm, const flo
   if (i >= n_valid) { lo[i] = -kInf; hi[i] = -kInf; return; }
   const float nx = norm[i];
   const float r = radii[i];
+  // strict '<' (prdc.py:37-48): nothing is closer than a zero radius.  Rows with k+1 exact duplicates
+  // have r = 0 and every one of their duplicate pairs would otherwise sit inside the band.
+  if (!(r > 0.f)) { lo[i] = -kInf; hi[i] = -kInf; return; }
   const float r2 = r * r;
   // band on the key plus slack for the fp32 rounding of r^2, |x|^2 and of the
   // final fp32 distance the refine kernel compares (3e-7 ~ 2.5 ulp)
@@ -264,6 +267,42 @@ prdc_exact_pairs_kernel(const T* __restrict__ R, long long ldr, const T* __restr
         atomicAdd(col_count + j, 1);
         row_cover[i - row0] = 1;
       }
+    }
+  }
+}
+
+// Exhaustive exact counts (no tensor-core filter, no list): the last rung of the overflow ladder —
+// when even a refine list sized to the reported number of near-tie pairs does not fit in memory.
+// Work item = (reference row, chunk of 1024 candidates), one warp each; the distance is formed by
+// the same warp routine as the refine kernels, so a pair decided here or there gets the same answer.
+template <typename T>
+__global__ void __launch_bounds__(256)
+prdc_bruteforce_counts_kernel(const T* __restrict__ R, long long ldr, const T* __restrict__ C, long long ldc, int d,
+                              long long m, const float* __restrict__ r_ref, const float* __restrict__ r_cand,
+                              long long row0, long long nrows, int32_t* __restrict__ col_count,
+                              uint8_t* __restrict__ row_recall, uint8_t* __restrict__ row_cover) {
+  const int lane = threadIdx.x & 31;
+  const long long chunks = (m + 1023) / 1024;
+  const long long items = nrows * chunks;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long it = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; it < items; it += warps) {
+    const long long row = it / chunks, j0 = (it - row * chunks) * 1024;
+    const long long i = row0 + row;
+    const float ri = r_ref[i];
+    const long long j1 = j0 + 1024 < m ? j0 + 1024 : m;
+    bool rec = false, cov = false;
+    for (long long j = j0; j < j1; ++j) {
+      const double d2 = exact_sqdist_warp(R + i * ldr, C + j * ldc, d, lane);
+      const float D = dist_f32(d2);
+      if (D < ri) {
+        cov = true;
+        if (lane == 0) atomicAdd(col_count + j, 1);
+      }
+      rec |= D < r_cand[j];
+    }
+    if (lane == 0) {
+      if (rec) row_recall[row] = 1;
+      if (cov) row_cover[row] = 1;
     }
   }
 }
@@ -364,7 +403,7 @@ constexpr int kTailSplitTopk = 1;
 constexpr int kTailSplitCount = 4;
 static int tail_split(int mode, int n_split, int n_ct, int want) {
   if (mode != 2 || n_split != 1 || n_ct < 64 * want) return n_split;
-  if (const char* e = getenv("AMB_TAIL_SPLIT")) return atoi(e) >= 1 && atoi(e) <= want ? atoi(e) : n_split;
+  if (const int v = option(kOptTailSplit)) return v >= 1 && v <= want ? v : n_split;
   return want;
 }
 
@@ -396,24 +435,21 @@ static KnnWs knn_ws(void* ws, long long nrows, int Kt, int n_split) {
 // product with a resident A panel (d <= 512), 2 = the same on CTA pairs (cta_group::2).
 static int engine_mode(int kb_count, long long row0) {
   if (kb_count > kMaxResidentKb) return 3;
-  const char* e = getenv("AMB_PASSES");
-  if (e && atoi(e) == 3) return 3;
-  const char* c = getenv("AMB_CTA2");   // AMB_CTA2=0: single-CTA kernel
-  const bool two = c ? atoi(c) != 0 : true;
+  if (option(kOptPasses) == 3) return 3;
+  const bool two = option(kOptCta2) != 0;   // engine_cta2 = 0: single-CTA kernel
   // the pair kernel takes A row tiles two at a time: the shard must start on an even tile
   return (two && (row0 / kTileM) % 2 == 0) ? 2 : 1;
 }
 
 // `counter`: a zeroed device int for the CTA-pair kernel's dynamic item hand-out
-// (AMB_SCHED=static keeps the round-robin assignment).
+// (option engine_static keeps the round-robin assignment).
 template <class Epi>
 static int run_engine(int mode, cudaStream_t st, int dev, EngineGeom g, const Epi& epi, const char* what,
                       double alg_pairs, int* counter) {
   if (mode == 3) return launch_engine(st, dev, g, epi, what, alg_pairs);
   if (mode == 1) return launch_engine1(st, dev, g, epi, what, alg_pairs);
   g.n_rt = (g.n_rt + 1) / 2;   // row-tile pairs
-  const char* e = getenv("AMB_SCHED");
-  g.work_counter = (e && e[0] == 's') ? nullptr : counter;
+  g.work_counter = option(kOptSchedStatic) ? nullptr : counter;
   return launch_engine2(st, dev, g, epi, what, alg_pairs);
 }
 
@@ -441,19 +477,26 @@ size_t amb_knn_ws_bytes(long long nrows, long long n, int d, int k) {
 }
 
 int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long long ld, const void* packed,
-                  long long n, int d, long long row0, long long nrows, int k, float* radii, void* ws,
-                  size_t ws_bytes) {
+                  long long n, int d, long long row0, long long nrows, int k, float* radii,
+                  long long* n_exhaustive, void* ws, size_t ws_bytes) {
   if (!X || !packed || !radii || n <= 0 || d <= 0 || nrows < 0 || row0 < 0 || row0 + nrows > n || ld < d)
     return set_error(AMB_ERR_ARG, "amb_knn_radii: bad argument");
   if (k < 1 || k + 1 > n)
     return set_error(AMB_ERR_ARG, "amb_knn_radii: k=%d needs at least k+1 rows (n=%lld); the reference's "
                                   "kthvalue raises here too", k, n);
+  if (nrows == 0) {   // an empty row shard (row0 == n is usually unaligned) is a valid no-op
+    if (n_exhaustive) {
+      DeviceGuard g0(dev);
+      if (!g0.ok) return AMB_ERR_CUDA;
+      return check_cuda(cudaMemsetAsync(n_exhaustive, 0, 8, static_cast<cudaStream_t>(stream)), "memset");
+    }
+    return AMB_OK;
+  }
   if (row0 % kTileM != 0) return set_error(AMB_ERR_ARG, "amb_knn_radii: row0 must be a multiple of 128");
   if (n >= (1ll << 31)) return set_error(AMB_ERR_ARG, "amb_knn_radii: n must be < 2^31");
   const int Kt = pick_kt(k);
   if (!Kt) return set_error(AMB_ERR_ARG, "amb_knn_radii: k=%d not supported (k <= 29)", k);
   if (dtype != AMB_F32 && dtype != AMB_F64) return set_error(AMB_ERR_ARG, "amb_knn_radii: bad dtype");
-  if (nrows == 0) return AMB_OK;
   DeviceGuard guard(dev);
   if (!guard.ok) return AMB_ERR_CUDA;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -461,8 +504,7 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
   const long long n_rt = (nrows + kTileM - 1) / kTileM;
   const long long n_ct = p.rows_pad / kTileN;
   int n_split = pick_split(dev, n_rt, n_ct, p.kb_count, 0);
-  if (const char* e = getenv("AMB_TOPK_SPLIT")) {   // tuning knob
-    const int v = atoi(e);
+  if (const int v = option(kOptTopkSplit)) {   // tuning knob
     if (v >= 1 && v <= 64 && v <= n_ct) n_split = v;
   }
   n_split = tail_split(engine_mode(p.kb_count, row0), n_split, static_cast<int>(n_ct), kTailSplitTopk);
@@ -499,27 +541,27 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
 
   const unsigned blocks = static_cast<unsigned>((nrows * 32 + 255) / 256);
   const int bf_blocks = 4 * sm_count(dev);
-  // brute-force budget: ~2e11 fp64 multiply-adds
-  long long max_rows = static_cast<long long>(2e11 / (static_cast<double>(n) * d));
-  if (max_rows > nrows) max_rows = nrows;
   if (dtype == AMB_F32) {
     const float* Xf = static_cast<const float*>(X);
     knn_refine_kernel<float><<<blocks, 256, 0, st>>>(Xf, ld, d, n, row0, nrows, k, Kt, 2 * n_split, list_rows, w.keys,
                                                      w.cols, p.norm, p.rho, sp, w.max_norm, radii, w.unresolved,
                                                      w.n_unresolved);
     if ((rc = check_launch("knn_refine_kernel"))) return rc;
-    knn_bruteforce_kernel<float><<<bf_blocks, 256, 0, st>>>(Xf, ld, d, n, row0, k, w.unresolved, w.n_unresolved,
-                                                            static_cast<int>(max_rows), radii);
+    knn_bruteforce_kernel<float><<<bf_blocks, 256, 0, st>>>(Xf, ld, d, n, row0, k, w.unresolved, w.n_unresolved, radii);
   } else {
     const double* Xd = static_cast<const double*>(X);
     knn_refine_kernel<double><<<blocks, 256, 0, st>>>(Xd, ld, d, n, row0, nrows, k, Kt, 2 * n_split, list_rows, w.keys,
                                                       w.cols, p.norm, p.rho, sp, w.max_norm, radii, w.unresolved,
                                                       w.n_unresolved);
     if ((rc = check_launch("knn_refine_kernel"))) return rc;
-    knn_bruteforce_kernel<double><<<bf_blocks, 256, 0, st>>>(Xd, ld, d, n, row0, k, w.unresolved, w.n_unresolved,
-                                                             static_cast<int>(max_rows), radii);
+    knn_bruteforce_kernel<double><<<bf_blocks, 256, 0, st>>>(Xd, ld, d, n, row0, k, w.unresolved, w.n_unresolved, radii);
   }
-  return check_launch("knn_bruteforce_kernel");
+  if ((rc = check_launch("knn_bruteforce_kernel"))) return rc;
+  if (n_exhaustive) {   // int32 counter -> caller's int64
+    if ((rc = check_cuda(cudaMemsetAsync(n_exhaustive, 0, 8, st), "memset"))) return rc;
+    rc = check_cuda(cudaMemcpyAsync(n_exhaustive, w.n_unresolved, 4, cudaMemcpyDeviceToDevice, st), "memcpy");
+  }
+  return rc;
 }
 
 long long amb_prdc_list_cap(long long n_ref, long long m) {
@@ -527,10 +569,25 @@ long long amb_prdc_list_cap(long long n_ref, long long m) {
   return cap < (1ll << 20) ? (1ll << 20) : cap;
 }
 
-size_t amb_prdc_ws_bytes(long long n_ref, long long m) {
-  if (n_ref <= 0 || m <= 0) return 0;
+// bytes of the workspace in front of the refine list: thresholds, chunk maxima, 512-byte header
+static size_t prdc_ws_fixed(long long n_ref, long long m) {
   const long long rp = round_up_ll(n_ref, kRowPad), cp = round_up_ll(m, kRowPad);
-  return static_cast<size_t>(round_up_ll((2 * rp + 2 * cp + cp / 32) * 4, 256) + 512 + amb_prdc_list_cap(n_ref, m) * 8);
+  return static_cast<size_t>(round_up_ll((2 * rp + 2 * cp + cp / 32) * 4, 256) + 512);
+}
+
+size_t amb_prdc_ws_bytes_cap(long long n_ref, long long m, long long list_cap) {
+  if (n_ref <= 0 || m <= 0 || list_cap < 1) return 0;
+  return prdc_ws_fixed(n_ref, m) + static_cast<size_t>(list_cap) * sizeof(PairEntry);
+}
+
+size_t amb_prdc_ws_bytes(long long n_ref, long long m) {
+  return amb_prdc_ws_bytes_cap(n_ref, m, amb_prdc_list_cap(n_ref, m));
+}
+
+long long amb_prdc_ws_list_cap(long long n_ref, long long m, size_t ws_bytes) {
+  if (n_ref <= 0 || m <= 0) return 0;
+  const size_t fixed = prdc_ws_fixed(n_ref, m);
+  return ws_bytes > fixed ? static_cast<long long>((ws_bytes - fixed) / sizeof(PairEntry)) : 0;
 }
 
 int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, const void* packed_ref,
@@ -541,15 +598,19 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   if (!R || !C || !packed_ref || !packed_cand || !r_ref || !r_cand || !col_count || !row_recall || !row_cover ||
       n_ref <= 0 || m <= 0 || d <= 0 || row0 < 0 || nrows < 0 || row0 + nrows > n_ref || ldr < d || ldc < d)
     return set_error(AMB_ERR_ARG, "amb_prdc_counts: bad argument");
-  if (row0 % kTileM != 0) return set_error(AMB_ERR_ARG, "amb_prdc_counts: row0 must be a multiple of 128");
   if (n_ref >= (1ll << 31) || m >= (1ll << 31)) return set_error(AMB_ERR_ARG, "amb_prdc_counts: sizes must be < 2^31");
   if (dtype != AMB_F32 && dtype != AMB_F64) return set_error(AMB_ERR_ARG, "amb_prdc_counts: bad dtype");
-  const size_t need = amb_prdc_ws_bytes(n_ref, m);
-  if (!ws || ws_bytes < need) return set_error(AMB_ERR_WS, "amb_prdc_counts: workspace %zu < %zu", ws_bytes, need);
-  if (nrows == 0) return AMB_OK;
   DeviceGuard guard(dev);
   if (!guard.ok) return AMB_ERR_CUDA;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nrows == 0) {   // an empty row shard (row0 == n_ref is usually unaligned) is a valid no-op
+    return n_uncertain ? check_cuda(cudaMemsetAsync(n_uncertain, 0, 8, st), "memset") : AMB_OK;
+  }
+  if (row0 % kTileM != 0) return set_error(AMB_ERR_ARG, "amb_prdc_counts: row0 must be a multiple of 128");
+  // the refine list takes whatever the workspace holds beyond the fixed part
+  const long long cap = amb_prdc_ws_list_cap(n_ref, m, ws_bytes);
+  if (!ws || cap < 1)
+    return set_error(AMB_ERR_WS, "amb_prdc_counts: workspace %zu < %zu", ws_bytes, amb_prdc_ws_bytes_cap(n_ref, m, 1));
   PackedPtrs pr = packed_ptrs(const_cast<void*>(packed_ref), n_ref, d);
   PackedPtrs pc = packed_ptrs(const_cast<void*>(packed_cand), m, d);
   // workspace carve-up
@@ -564,7 +625,6 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   float* max_ref = reinterpret_cast<float*>(q + 64);
   float* max_cand = reinterpret_cast<float*>(q + 128);
   PairEntry* list = reinterpret_cast<PairEntry*>(q + 512);
-  const long long cap = amb_prdc_list_cap(n_ref, m);
 
   int rc;
   if ((rc = check_cuda(cudaMemsetAsync(q, 0, 512, st), "memset"))) return rc;
@@ -598,8 +658,7 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   // the single-pass kernel keeps the A panel in shared memory: no L2 pressure from A, one split
   g.n_split = pick_split(dev, g.n_rt, g.n_ct, pc.kb_count, sp ? 0 : kCountSplitBytes);
   g.n_split = tail_split(mode, g.n_split, g.n_ct, kTailSplitCount);
-  if (const char* e = getenv("AMB_COUNT_SPLIT")) {   // tuning knob
-    const int v = atoi(e);
+  if (const int v = option(kOptCountSplit)) {   // tuning knob
     if (v >= 1 && v <= 64 && v <= g.n_ct) g.n_split = v;
   }
   g.lbo_bytes = 128;
@@ -622,6 +681,33 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr, 
   if (n_uncertain)
     rc = check_cuda(cudaMemcpyAsync(n_uncertain, list_count, 8, cudaMemcpyDeviceToDevice, st), "memcpy");
   return rc;
+}
+
+int amb_prdc_counts_exact(int dev, amb_stream_t stream, const void* R, long long ldr, long long n_ref,
+                          const float* r_ref, const void* C, long long ldc, long long m, const float* r_cand,
+                          int d, int dtype, long long row0, long long nrows, int32_t* col_count,
+                          uint8_t* row_recall, uint8_t* row_cover) {
+  if (!R || !C || !r_ref || !r_cand || !col_count || !row_recall || !row_cover || n_ref <= 0 || m <= 0 || d <= 0 ||
+      row0 < 0 || nrows < 0 || row0 + nrows > n_ref || ldr < d || ldc < d)
+    return set_error(AMB_ERR_ARG, "amb_prdc_counts_exact: bad argument");
+  if (dtype != AMB_F32 && dtype != AMB_F64) return set_error(AMB_ERR_ARG, "amb_prdc_counts_exact: bad dtype");
+  if (nrows == 0) return AMB_OK;
+  DeviceGuard guard(dev);
+  if (!guard.ok) return AMB_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = check_cuda(cudaMemsetAsync(row_recall, 0, nrows, st), "memset"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(row_cover, 0, nrows, st), "memset"))) return rc;
+  const int blocks = 8 * sm_count(dev);
+  if (dtype == AMB_F32)
+    prdc_bruteforce_counts_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(R), ldr,
+                                                                 static_cast<const float*>(C), ldc, d, m, r_ref, r_cand,
+                                                                 row0, nrows, col_count, row_recall, row_cover);
+  else
+    prdc_bruteforce_counts_kernel<double><<<blocks, 256, 0, st>>>(static_cast<const double*>(R), ldr,
+                                                                  static_cast<const double*>(C), ldc, d, m, r_ref, r_cand,
+                                                                  row0, nrows, col_count, row_recall, row_cover);
+  return check_launch("prdc_bruteforce_counts_kernel");
 }
 
 int amb_prdc_reduce(int dev, amb_stream_t stream, const int32_t* col_count, long long m,

@@ -1,31 +1,43 @@
-"""Row-sharded evaluation of FAD / KD / PRDC across the GPUs of one box.
+"""The fused evaluation step: FAD / KD / PRDC / APA of (reference, candidate) in one
+asynchronous schedule with a single read-back, on one GPU or row-sharded across the
+GPUs of one box.
 
 One process per GPU (``torch.distributed``, NCCL over NVLink).  Every sub-path is
 row-independent, so the only exchanges are:
 
-  covariance   allreduce(sum) of the fp64 raw moments [sum | gram] of both sets
+  covariance   allreduce(sum) of the fp64 raw moments [sum | gram] of every set (one message)
   embeddings   allgather of the row shards (every rank needs all columns)
   radii        allgather of each rank's slice of k-NN radii
-  counts       allreduce(sum) of the per-candidate counts and of two row totals
+  counts       allreduce(sum) of the per-candidate counts and of two row totals,
+               allreduce(max) of the per-rank near-tie counts (refine-list overflow check)
   KD           subsets dealt round-robin to ranks, allgather of the 100 MMD values
 
 Row shards are contiguous and aligned to 256 rows (two tensor-core row tiles).
+Two front ends share the schedule:
+
+  evaluate_sharded      raw row shards (tensors) in, result dict out
+  evaluate_containers   AudioMetricsData containers in (what ``AudioMetrics.evaluate``
+                        calls): statistics, gathered sets, packed operands and k-NN radii
+                        are cached on the containers, so a reference set is swept once
+
 The arithmetic is delegated to an ``ops`` object so that the sharding and
 reduction logic can be exercised on CPU (gloo, world_size 2) in the test-suite
 with stand-in kernels; the product ``CudaOps`` calls the C ABI and nothing else.
 """
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
-_SIDE_STREAMS = {}
 ROW_ALIGN = 256     # two row tiles: shards start on an even tile, so the CTA-pair engine applies
+EXACT = "exact"     # refine-list capacity value that selects the exhaustive count kernel
 
 
 def shard_rows(n: int, world: int, rank: int):
-    """(row0, nrows, chunk): contiguous 128-aligned row range of ``rank``."""
+    """(row0, nrows, chunk): contiguous 256-aligned row range of ``rank``."""
     chunk = -(-n // world)
     chunk = -(-chunk // ROW_ALIGN) * ROW_ALIGN
     row0 = min(rank * chunk, n)
@@ -50,17 +62,23 @@ def _allgather_rows(x: torch.Tensor, n: int, chunk: int, group):
     return out[:n]
 
 
-def _null():
-    import contextlib
-
-    return contextlib.nullcontext()
-
-
-def _allreduce(t: torch.Tensor, group):
+def _allreduce(t: torch.Tensor, group, op=None):
     world, _ = _world(group)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=group)
     return t
+
+
+@functools.lru_cache(maxsize=8)
+def kd_subset_indices(n1: int, n2: int, m: int, subsets: int, seed: int) -> np.ndarray:
+    """The index stream of kd.py:176,185-186 ([S, 2, m] int32).  It depends only on the set sizes
+    and the seed, so repeated evaluations against the same sizes draw it once (200 numpy
+    ``choice`` calls: about 4 ms at 200k rows)."""
+    from .metrics.kd import draw_subset_indices
+
+    idx = draw_subset_indices(n1, n2, m, subsets, seed)
+    idx.setflags(write=False)
+    return idx
 
 
 class CudaOps:
@@ -71,59 +89,7 @@ class CudaOps:
 
         self._lib = _lib
         self.device = _lib.require_cuda(device)
-        self._side = None
-
-    # -- the N-independent FAD kernels (Cholesky, Jacobi: ~30 CTAs, latency-bound) run on a
-    #    high-priority side stream beside the PRDC sweeps, whose CTA pairs take their work
-    #    items dynamically and simply give up the SMs the side stream is holding
-    def side(self, *tensors):
-        import contextlib
-
-        @contextlib.contextmanager
-        def ctx():
-            if self._side is None:
-                # ONE side stream per device for the life of the process: torch hands out pooled
-                # streams round-robin, and a fresh one per call eventually lands on the hardware queue
-                # of the main stream, which serialises the two (seen as 100-200 ms outlier steps)
-                key = self.device.index
-                if key not in _SIDE_STREAMS:
-                    _SIDE_STREAMS[key] = torch.cuda.Stream(self.device, priority=-1)
-                self._side = _SIDE_STREAMS[key]
-            main = torch.cuda.current_stream(self.device)
-            self._side.wait_stream(main)
-            # (no record_stream: the caller keeps `tensors` alive until join(), and marking them would
-            #  make the caching allocator hold their blocks back across streams)
-            L = self._lib.lib()
-            L.amb_set_option(b"fad_ctas", self.SHARED_SMS)     # the sweep beside it leaves these SMs alone
-            try:
-                with torch.cuda.stream(self._side):
-                    if self.trace is not None:
-                        e0 = torch.cuda.Event(enable_timing=True); e0.record()
-                    yield
-                    if self.trace is not None:
-                        e1 = torch.cuda.Event(enable_timing=True); e1.record()
-                        self.trace.append((e0, e1))
-            finally:
-                L.amb_set_option(b"fad_ctas", 0)
-        return ctx()
-
-    import os as _os
-    SHARED_SMS = int(_os.environ.get("AMB_SHARED_SMS", "16"))
-    trace = None     # set to a list to collect (start, end) CUDA events of the side-stream section
-
-    def reserve_sms(self, on):
-        """The next all-pairs sweeps leave SHARED_SMS SMs to the side stream (on) / use them all (off)."""
-        self._lib.lib().amb_set_option(b"engine_reserve_sms", self.SHARED_SMS if on else 0)
-
-    def use_side(self):
-        import os
-
-        return os.environ.get("AMB_FAD_SIDE", "1") != "0"
-
-    def join(self, *tensors):
-        if self._side is not None:
-            main = torch.cuda.current_stream(self.device)
-            main.wait_stream(self._side)
+        self._idx_dev = {}
 
     def moments(self, x):
         """fp64 [d + d*d] raw moments (column sums | Gram) of a row shard."""
@@ -145,16 +111,15 @@ class CudaOps:
                                            buf[d:].data_ptr(), mean.data_ptr(), cov.data_ptr()))
         return mean, cov
 
-    def frechet(self, sx, sy):
+    def frechet_batch(self, pairs):
+        """[(stats_x, stats_y)] with stats = (mean, cov) -> fp64 device tensor [len(pairs)], no sync."""
         from .metrics.fad import frechet_distances
 
         class _S:
-            pass
+            def __init__(self, s):
+                self.mean, self.cov = s
 
-        a, b = _S(), _S()
-        a.mean, a.cov = sx
-        b.mean, b.cov = sy
-        return frechet_distances([(a, b)], device=self.device, as_tensor=True)[0]   # stays on the device
+        return frechet_distances([(_S(a), _S(b)) for a, b in pairs], device=self.device, as_tensor=True)
 
     def container(self, x):
         from .data import AudioMetricsData
@@ -168,35 +133,224 @@ class CudaOps:
 
         return nearest_neighbour_distances(c, k, row_range=(row0, nrows))
 
-    def count_rows(self, cref, ccand, r_ref, r_cand, row0, nrows, k):
-        """(col_count [m] int32, totals int64 [n_recalled, n_covered, n_uncertain])."""
+    def count_rows(self, cref, ccand, r_ref, r_cand, row0, nrows, k, list_cap=None):
+        """(col_count [m] int32, int64 [n_recalled, n_covered], int64 [n_uncertain, list capacity])
+        for one shard of reference rows; ``list_cap`` as metrics.prdc.prdc_totals."""
         from .metrics.prdc import prdc_totals
 
         col, rec, cov, totals = prdc_totals(cref, ccand, k, row_range=(row0, nrows), ref_radii=r_ref,
-                                            cand_radii=r_cand)
-        t = torch.stack([rec.sum(dtype=torch.int64), cov.sum(dtype=torch.int64), totals[4]])
-        return col, t
+                                            cand_radii=r_cand, list_cap=list_cap)
+        return col, torch.stack([rec.sum(dtype=torch.int64), cov.sum(dtype=torch.int64)]), totals[4:6]
 
-    def check_uncertain(self, uncertain, n_ref, n_cand):
-        """The refine list has a fixed capacity; pairs beyond it were not re-decided."""
-        cap = self._lib.lib().amb_prdc_list_cap(n_ref, n_cand)
-        if uncertain > cap * max(1, _world(None)[0]):
-            raise self._lib.AmbError(f"{uncertain} near-tie pairs exceed the refine list capacity {cap}")
+    def next_list_cap(self, uncertain, n_ref, n_cand):
+        from .metrics.prdc import next_list_cap
 
-    def kd_mmds(self, f1, f2, idx, gamma, coef0, degree):
+        return next_list_cap(uncertain, n_ref, n_cand, self.device)
+
+    def kd_mmds(self, f1, f2, idx, gamma, coef0, degree, key=None):
         L, dev = self._lib.lib(), self.device
         S, _, m = idx.shape
         out = torch.empty(S, dtype=torch.float64, device=dev)
         if S == 0:
             return out
-        idx_dev = torch.from_numpy(np.ascontiguousarray(idx)).to(dev)
+        idx_dev = self._idx_dev.get(key) if key is not None else None
+        if idx_dev is None:
+            idx_dev = torch.from_numpy(np.array(idx, copy=True)).to(dev)
+            if key is not None:
+                self._idx_dev = {key: idx_dev}     # keep the last one: same sizes evaluate after evaluate
         ws = self._lib.workspace(L.amb_kd_ws_bytes(S, m, f1.shape[1]), dev)
         self._lib.check(L.amb_kd_subsets(dev.index, self._lib.stream_ptr(dev), f1.data_ptr(), f1.shape[0],
                                          f1.stride(0), f2.data_ptr(), f2.shape[0], f2.stride(0), f1.shape[1],
                                          self._lib.dtype_code(f1), idx_dev.data_ptr(), S, m, self._lib.AMB_KERNEL_POLY,
-                                         float(gamma), float(coef0), int(degree), 1.0, out.data_ptr(), None,
-                                         ws.data_ptr(), ws.numel()))
+                                         float(gamma), float(coef0), int(degree), 1.0, self._lib.AMB_MMD_UNBIASED,
+                                         out.data_ptr(), None, ws.data_ptr(), ws.numel()))
         return out
+
+
+_OPS = {}
+
+
+def default_ops(device=None):
+    """One CudaOps per device (it only caches the uploaded KD index tensor)."""
+    from . import _lib
+
+    dev = _lib.require_cuda(device)
+    ops = _OPS.get(dev.index)
+    if ops is None:
+        ops = _OPS[dev.index] = CudaOps(dev)
+    return ops
+
+
+class _Shard:
+    """A row shard handed in as a plain tensor (evaluate_sharded)."""
+
+    def __init__(self, rows, n_total, ops, ready=None):
+        self.rows_, self.n_total, self.ops, self.ready = rows, n_total, ops, ready
+        self.cache = {}
+        self.d = rows.shape[1]
+        self.device = rows.device
+
+    def rows(self):
+        if self.ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.ready)
+            self.ready = None
+        return self.rows_
+
+    def moments(self):
+        return self.ops.moments(self.rows())
+
+    def full_container(self, gathered):
+        return self.ops.container(gathered)
+
+
+class _Held:
+    """A row shard held by an AudioMetricsData (evaluate_containers): statistics come from the
+    container, derived data is cached on it and dropped when rows are added."""
+
+    def __init__(self, c, n_total, ops):
+        self.c, self.n_total, self.ops = c, n_total, ops
+        self.cache = c._cache
+        mean = c.mean if c._buf is None else None
+        self.d = c._buf.shape[1] if c._buf is not None else mean.shape[0]
+        self.device = c.device
+
+    def rows(self):
+        x = self.c.embeddings
+        if x is None:
+            raise ValueError("this metric needs stored embeddings (store_embeddings=True)")
+        return x
+
+    def moments(self):
+        return self.c.local_moments()
+
+    def full_container(self, gathered):
+        return self.c if gathered is None else self.ops.container(gathered)
+
+
+def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=100, kd_subset_size=1000,
+           kd_seed=1234):
+    """The schedule.  ``ref`` / ``cand``: _Shard or _Held.  ``extra_fad``: [(name, x, y)] further
+    Frechet distances (x, y: _Held) evaluated in the same batched launch (APA)."""
+    from .metrics.kd import KID_COEF0, KID_DEGREE
+
+    world, rank = _world(group)
+    want_fad, want_kd, want_prdc = "fad" in metrics, "kd" in metrics, "prdc" in metrics
+    pending = {}
+    n_ref, n_cand = (ref.n_total, cand.n_total) if ref is not None else (0, 0)
+    k = nearest_k if nearest_k is not None else max(1, min(10, n_ref, n_cand))   # audio_metrics.py:263
+    d = ref.d if ref is not None else None
+
+    def full(s, n):
+        """(container over ALL rows of the set, this rank's row range) — gathered once per set."""
+        key = ("full", world, id(group))
+        hit = s.cache.get(key)
+        if hit is None:
+            row0, nrows, chunk = shard_rows(n, world, rank)
+            rows = s.rows()
+            assert rows.shape[0] == nrows, "shards must follow shard_rows()"
+            gathered = None if world == 1 and isinstance(s, _Held) else _allgather_rows(rows, n, chunk, group)
+            hit = s.cache[key] = (s.full_container(gathered), row0, nrows, chunk)
+        return hit
+
+    def radii(s, n):
+        c, row0, nrows, chunk = full(s, n)
+        key = f"radii_{k}"
+        r = c.radii.get(key)
+        if r is None:
+            r = _allgather_rows(ops.radii_rows(c, row0, nrows, k), n, chunk, group).contiguous()
+            c.radii[key] = r
+        return r
+
+    # ---- reference-only work first: a candidate whose host-to-device copy is still in flight is
+    #      touched as late as possible
+    stat_sets, fad_pairs = [], []
+    if want_fad:
+        fad_pairs.append(("fad", cand, ref))                    # (cand, ref) as audio_metrics.py:257
+    fad_pairs.extend(extra_fad)
+    for _, x, y in fad_pairs:
+        for s in (y, x):                                        # references before candidates
+            if all(s is not t for t in stat_sets):
+                stat_sets.append(s)
+    stat_sets.sort(key=lambda s: s is cand)                     # the candidate's moments last
+    moms = []
+    done_ref_sweep = False
+    for s in stat_sets:
+        if s is cand and want_prdc and not done_ref_sweep:
+            r_ref = radii(ref, n_ref)
+            done_ref_sweep = True
+        moms.append(s.moments())
+    if want_prdc and not done_ref_sweep:
+        r_ref = radii(ref, n_ref)
+    if fad_pairs:
+        sizes = [s.d + s.d * s.d for s in stat_sets]
+        mom = torch.cat(moms) if len(moms) > 1 else moms[0]
+        _allreduce(mom, group)                                  # one message: sum of (d + d^2) doubles per set
+        stats, off = [], 0
+        for s, sz in zip(stat_sets, sizes):
+            stats.append(ops.stats_from_moments(mom[off:off + sz], s.n_total, s.d))
+            off += sz
+        lookup = lambda s: stats[[t is s for t in stat_sets].index(True)]
+        pending["fad"] = ops.frechet_batch([(lookup(x), lookup(y)) for _, x, y in fad_pairs])
+        pending["_mom"] = mom
+
+    # ---- PRDC
+    def counts(list_cap):
+        cref, r_row0, r_nrows, _ = full(ref, n_ref)
+        ccand = full(cand, n_cand)[0]
+        col, t, unc = ops.count_rows(cref, ccand, r_ref, r_cand, r_row0, r_nrows, k, list_cap=list_cap)
+        _allreduce(col, group)                                  # [m] int32
+        _allreduce(t, group)                                    # 2 int64
+        unc = unc.clone()
+        _allreduce(unc, group, dist.ReduceOp.MAX if world > 1 else None)   # worst rank decides: lists are per rank
+        return torch.cat([torch.stack([(col > 0).sum(dtype=torch.int64), col.sum(dtype=torch.int64)]),
+                          t.to(torch.int64), unc.to(torch.int64)])
+
+    if want_prdc:
+        r_cand = radii(cand, n_cand)
+        pending["prdc"] = counts(None)
+
+    # ---- KD: subsets dealt round-robin to the ranks
+    if want_kd:
+        n_s = min(n_ref, n_cand)
+        m = kd_subset_size if kd_subset_size < n_s else max(1, n_s // 2)        # kd.py:160-168
+        idx = kd_subset_indices(n_cand, n_ref, m, kd_subsets, kd_seed)           # features_1 = candidate
+        mine = idx[rank::world]
+        per = -(-kd_subsets // world)
+        f1, f2 = full(cand, n_cand)[0].embeddings, full(ref, n_ref)[0].embeddings
+        local = ops.kd_mmds(f1, f2, mine, 1.0 / d, KID_COEF0, KID_DEGREE,
+                            key=(n_cand, n_ref, m, kd_subsets, kd_seed, rank, world))
+        if world > 1:
+            pad = torch.zeros(per, dtype=torch.float64, device=local.device)
+            pad[: local.shape[0]] = local
+            allv = torch.empty(world * per, dtype=torch.float64, device=local.device)
+            dist.all_gather_into_tensor(allv, pad, group=group)
+            order = torch.tensor([(s % world) * per + s // world for s in range(kd_subsets)], device=local.device)
+            pending["kd"] = allv[order]
+        else:
+            pending["kd"] = local
+
+    # ---- the one read-back
+    result = {}
+    if fad_pairs:
+        vals = pending["fad"].tolist()
+        for (name, _, _), v in zip(fad_pairs, vals):
+            result[name] = float(v)
+    if want_kd:
+        mm = pending["kd"].cpu().numpy()
+        result["kernel_distance_mean"] = float(np.mean(mm))                       # kd.py:190
+        result["kernel_distance_std"] = float(np.std(mm))                         # kd.py:191
+    if want_prdc:
+        hits, total, recalled, covered, uncertain, cap = pending["prdc"].tolist()
+        list_cap = None
+        while list_cap != EXACT and uncertain > cap:
+            # More near-tie pairs than the refine list of some rank holds (prdc.py:18-50 has no such
+            # limit): repeat the count sweep with a list of the reported size, or exhaustively.
+            # Every rank sees the same reduced numbers, so all of them take this branch together.
+            list_cap = ops.next_list_cap(uncertain, n_ref, n_cand)
+            hits, total, recalled, covered, uncertain, cap = counts(list_cap).tolist()
+        result.update(precision=hits / n_cand, recall=recalled / n_ref,
+                      density=(1.0 / float(k)) * (total / n_cand), coverage=covered / n_ref)   # prdc.py:36-48
+    return result
 
 
 def evaluate_sharded(ref_shard, cand_shard, n_ref, n_cand, metrics=("fad", "kd", "prdc"), nearest_k=5,
@@ -209,120 +363,56 @@ def evaluate_sharded(ref_shard, cand_shard, n_ref, n_cand, metrics=("fad", "kd",
     single-GPU path.
 
     Everything is enqueued without a host synchronisation and read back once at the
-    end (the reference makes one ``.item()`` per metric): the KD subset indices are
-    drawn on the host (numpy, kd.py:176-186) while the GPU is busy with PRDC.
+    end (the reference makes one ``.item()`` per metric).
     ``ready = (event_ref, event_cand)`` (CUDA events, either may be None) lets the caller
     hand over shards whose host-to-device copies are still in flight on another stream:
     all reference-only work (moments, packing, radii) is queued before the candidate
     shard is first touched.
     """
-    from .metrics.kd import draw_subset_indices, KID_DEGREE, KID_COEF0
-
-    ops = ops or CudaOps()
+    ops = ops or default_ops(ref_shard.device if ref_shard.is_cuda else None)
     world, rank = _world(group)
-    d = ref_shard.shape[1]
-    r_row0, r_nrows, r_chunk = shard_rows(n_ref, world, rank)
-    c_row0, c_nrows, c_chunk = shard_rows(n_cand, world, rank)
-    assert ref_shard.shape[0] == r_nrows and cand_shard.shape[0] == c_nrows, "shards must follow shard_rows()"
-    want_fad, want_kd, want_prdc = "fad" in metrics, "kd" in metrics, "prdc" in metrics
-    k = nearest_k
-
-    def wait(ev):
-        if ev is not None:
-            torch.cuda.current_stream(ref_shard.device).wait_event(ev)
-
+    assert ref_shard.shape[0] == shard_rows(n_ref, world, rank)[1], "shards must follow shard_rows()"
+    assert cand_shard.shape[0] == shard_rows(n_cand, world, rank)[1], "shards must follow shard_rows()"
     ev_ref, ev_cand = ready if ready is not None else (None, None)
-    pending = {}                                     # device-side results, read back at the end
+    return _fused(ops, _Shard(ref_shard, n_ref, ops, ev_ref), _Shard(cand_shard, n_cand, ops, ev_cand), metrics,
+                  nearest_k, group, kd_subsets=kd_subsets, kd_subset_size=kd_subset_size, kd_seed=kd_seed)
 
-    overlap = want_fad and want_prdc and hasattr(ops, "side") and ops.use_side()   # alone, FAD runs at full width
-    # One GPU: reference-only work first, so that a candidate shard still in flight (ready=) is touched
-    # late; the FAD kernels then run beside the candidate radii sweep.  Several GPUs: the sweeps are
-    # 1/world as long while FAD is N-independent, so FAD is started first and all sweeps leave it room.
-    fad_first = overlap and world > 1
 
-    def fad(mom_ref, mom_cand):
-        mom = torch.cat([mom_ref, mom_cand])
-        _allreduce(mom, group)                       # one message: 2 (d + d^2) doubles
-        half = d + d * d
-        with ops.side(mom) if overlap else _null():
-            s_ref = ops.stats_from_moments(mom[:half], n_ref, d)
-            s_cand = ops.stats_from_moments(mom[half:], n_cand, d)
-            pending["fad"] = ops.frechet(s_cand, s_ref)  # (cand, ref) as audio_metrics.py:257
-        pending["_mom"] = mom                        # alive until the read-back (used on the side stream)
+def evaluate_containers(ref, cand, metrics=("fad", "kd", "prdc"), nearest_k=5, group=None, apa=None,
+                        kd_subsets=100, kd_subset_size=1000, kd_seed=1234):
+    """The same step on AudioMetricsData containers — what ``AudioMetrics.evaluate`` runs.
 
-    def narrowed(on):
-        if overlap:
-            ops.reserve_sms(on)
+    ``ref`` / ``cand`` hold this rank's rows (all rows when no process group is initialised).
+    ``apa = (apa_cand, apa_ref, apa_anti, d_x_xp)``: the mix containers of the APA score; their
+    Frechet distances join the same batched launch, the result dict then carries "_d_y_x",
+    "_d_y_xp" and (when ``d_x_xp`` is None) "_d_x_xp" for apa.py:22-32 to combine.
+    ``ref`` / ``cand`` may be None when only APA is wanted.
+    """
+    some = ref if ref is not None else apa[0]
+    ops = default_ops(some.device)
+    world, _ = _world(group)
 
-    # ---- reference-only work
-    wait(ev_ref)
-    if want_fad:
-        mom_ref = ops.moments(ref_shard)
-    if fad_first:
-        wait(ev_cand)
-        fad(mom_ref, ops.moments(cand_shard))
-    if want_kd or want_prdc:
-        ref = _allgather_rows(ref_shard, n_ref, r_chunk, group)
-    try:
-        if want_prdc:
-            cref = ops.container(ref)
-            if fad_first:
-                cref.packed()
-                narrowed(True)
-            r_ref = _allgather_rows(ops.radii_rows(cref, r_row0, r_nrows, k), n_ref, r_chunk, group).contiguous()
+    def total(c):
+        if world == 1:
+            return c.n
+        t = torch.tensor([c.n or 0], dtype=torch.int64, device=ops.device)
+        _allreduce(t, group)
+        return int(t)
 
-        # ---- candidate
-        wait(ev_cand)
-        if want_fad and not fad_first:
-            fad(mom_ref, ops.moments(cand_shard))
-        if want_kd or want_prdc:
-            cand = _allgather_rows(cand_shard, n_cand, c_chunk, group)
-        if want_prdc:
-            ccand = ops.container(cand)
-            if overlap and not fad_first:
-                ccand.packed()            # (the pack kernels are not part of the sweep that shares the GPU)
-                narrowed(True)            # FAD (about 20 ms) runs beside the candidate radii sweep (about 35 ms)
-            r_cand = _allgather_rows(ops.radii_rows(ccand, c_row0, c_nrows, k), n_cand, c_chunk, group).contiguous()
-            if not fad_first:
-                narrowed(False)           # ... and the count sweep is full width again
-            col, t = ops.count_rows(cref, ccand, r_ref, r_cand, r_row0, r_nrows, k)
-            _allreduce(col, group)                       # [m] int32
-            _allreduce(t, group)                         # 3 int64
-            pending["prdc"] = torch.cat([torch.stack([(col > 0).sum(dtype=torch.int64), col.sum(dtype=torch.int64)]),
-                                         t.to(torch.int64)])
-    finally:
-        narrowed(False)
+    def held(c):
+        hit = c._cache.get(("held", world, id(group)))
+        if hit is None or hit.n_total is None:
+            hit = c._cache[("held", world, id(group))] = _Held(c, total(c), ops)
+        return hit
 
-    if want_kd:
-        n_s = min(n_ref, n_cand)
-        m = kd_subset_size if kd_subset_size < n_s else max(1, n_s // 2)        # kd.py:160-168
-        idx = draw_subset_indices(n_cand, n_ref, m, kd_subsets, kd_seed)         # features_1 = candidate
-        mine = idx[rank::world]
-        per = -(-kd_subsets // world)
-        local = ops.kd_mmds(cand, ref, mine, 1.0 / d, KID_COEF0, KID_DEGREE)
-        if world > 1:
-            pad = torch.zeros(per, dtype=torch.float64, device=local.device)
-            pad[: local.shape[0]] = local
-            allv = torch.empty(world * per, dtype=torch.float64, device=local.device)
-            dist.all_gather_into_tensor(allv, pad, group=group)
-            order = torch.tensor([(s % world) * per + s // world for s in range(kd_subsets)], device=local.device)
-            pending["kd"] = allv[order]
-        else:
-            pending["kd"] = local
-
-    # ---- the one read-back
-    if want_fad and hasattr(ops, "join"):
-        ops.join(pending["fad"])
-    result = {}
-    if want_fad:
-        result["fad"] = float(pending["fad"])
-    if want_kd:
-        mm = pending["kd"].cpu().numpy()
-        result["kernel_distance_mean"] = float(np.mean(mm))                       # kd.py:190
-        result["kernel_distance_std"] = float(np.std(mm))                         # kd.py:191
-    if want_prdc:
-        hits, total, recalled, covered, uncertain = pending["prdc"].tolist()
-        ops.check_uncertain(uncertain, n_ref, n_cand)
-        result.update(precision=hits / n_cand, recall=recalled / n_ref,
-                      density=(1.0 / float(k)) * (total / n_cand), coverage=covered / n_ref)   # prdc.py:36-48
-    return result
+    extra = []
+    if apa is not None:
+        a_cand, a_ref, a_anti, d_x_xp = apa
+        extra = [("_d_y_x", held(a_cand), held(a_ref)), ("_d_y_xp", held(a_cand), held(a_anti))]
+        if d_x_xp is None:
+            extra.append(("_d_x_xp", held(a_ref), held(a_anti)))
+    if ref is None:
+        metrics = ()
+    return _fused(ops, held(ref) if ref is not None else None, held(cand) if cand is not None else None, metrics,
+                  nearest_k, group, extra_fad=extra, kd_subsets=kd_subsets, kd_subset_size=kd_subset_size,
+                  kd_seed=kd_seed)

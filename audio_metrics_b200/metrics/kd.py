@@ -39,9 +39,43 @@ def draw_subset_indices(n1, n2, m, subsets, seed):
     return idx
 
 
+_MMD_EST = {"unbiased": _lib.AMB_MMD_UNBIASED, "biased": _lib.AMB_MMD_BIASED, "u-statistic": _lib.AMB_MMD_USTAT}
+
+
+def mmd2(K_XX, K_XY, K_YY, unit_diagonal=False, mmd_est="unbiased"):
+    """kd.py:38-83 on precomputed m x m kernel matrices (arrays or tensors), fp64 on the device.
+    ``kid_features_to_metric(..., mmd_est=...)`` evaluates the same three estimators without ever
+    forming the matrices; this function exists for callers that already hold them."""
+    assert mmd_est in _MMD_EST, "Invalid value of mmd_est"                   # kd.py:39-43
+    dev = _lib.require_cuda(K_XX.device if isinstance(K_XX, torch.Tensor) and K_XX.is_cuda else None)
+    K_XX, K_XY, K_YY = (torch.as_tensor(k).to(dev, torch.float64) for k in (K_XX, K_XY, K_YY))
+    m = K_XX.shape[0]
+    assert K_XX.shape == (m, m) and K_XY.shape == (m, m) and K_YY.shape == (m, m)   # kd.py:45-48
+    if unit_diagonal:
+        diag_X = diag_Y = torch.ones((), dtype=torch.float64, device=dev)
+        sum_diag_X = sum_diag_Y = float(m)
+    else:
+        diag_X, diag_Y = K_XX.diagonal(), K_YY.diagonal()
+        sum_diag_X, sum_diag_Y = diag_X.sum(), diag_Y.sum()
+    Kt_XX_sum = (K_XX.sum(dim=1) - diag_X).sum()
+    Kt_YY_sum = (K_YY.sum(dim=1) - diag_Y).sum()
+    K_XY_sum = K_XY.sum(dim=0).sum()
+    if mmd_est == "biased":
+        out = (Kt_XX_sum + sum_diag_X) / (m * m) + (Kt_YY_sum + sum_diag_Y) / (m * m) - 2 * K_XY_sum / (m * m)
+    else:
+        out = (Kt_XX_sum + Kt_YY_sum) / (m * (m - 1))
+        if mmd_est == "unbiased":
+            out = out - 2 * K_XY_sum / (m * m)
+        else:
+            out = out - 2 * (K_XY_sum - K_XY.trace()) / (m * (m - 1))
+    return float(out)
+
+
 def kid_features_to_metric(features_1, features_2, **kwargs):
     """kd.py:127-194 with the same keyword arguments; ``return_mmds=True`` adds the
-    per-subset values under "mmds"."""
+    per-subset values under "mmds".  Two further keywords select what the reference only
+    reaches through ``mmd2`` (kd.py:38-83): ``mmd_est`` in ("unbiased", "biased",
+    "u-statistic") and ``unit_diagonal``."""
     kernel_type = kwargs.get("kernel_type", "polynomial")
     if kernel_type == "polynomial":
         ktype = _lib.AMB_KERNEL_POLY
@@ -77,16 +111,25 @@ def kid_features_to_metric(features_1, features_2, **kwargs):
     degree = int(kwargs.get("kid_degree", KID_DEGREE))
     coef0 = float(kwargs.get("kid_coef0", KID_COEF0))
     sigma = float(kwargs.get("kid_sigma", KID_SIGMA))
+    mmd_est = kwargs.get("mmd_est", "unbiased")
+    assert mmd_est in _MMD_EST, "Invalid value of mmd_est"                   # kd.py:39-43
+    est = _MMD_EST[mmd_est] | (_lib.AMB_MMD_UNIT_DIAGONAL if kwargs.get("unit_diagonal", False) else 0)
 
-    idx = draw_subset_indices(n1, n2, kid_subset_size, kid_subsets, kwargs.get("rng_seed", 1234))
-    idx_dev = torch.from_numpy(idx).to(dev, non_blocking=True)
+    from ..dist import kd_subset_indices
+
+    seed = kwargs.get("rng_seed", 1234)
+    if seed is None:       # numpy then seeds from the OS: a fresh draw every call, nothing to cache
+        idx = draw_subset_indices(n1, n2, int(kid_subset_size), int(kid_subsets), None)
+    else:
+        idx = kd_subset_indices(n1, n2, int(kid_subset_size), int(kid_subsets), int(seed))
+    idx_dev = torch.from_numpy(np.array(idx, copy=True)).to(dev, non_blocking=True)
     L = _lib.lib()
     mmds = torch.empty(kid_subsets, dtype=torch.float64, device=dev)
     stats = torch.empty(2, dtype=torch.float64, device=dev)
     ws = _lib.workspace(L.amb_kd_ws_bytes(kid_subsets, kid_subset_size, d), dev)
     _lib.check(L.amb_kd_subsets(dev.index, _lib.stream_ptr(dev), f1.data_ptr(), n1, f1.stride(0), f2.data_ptr(), n2,
                                 f2.stride(0), d, _lib.dtype_code(f1), idx_dev.data_ptr(), kid_subsets,
-                                kid_subset_size, ktype, float(gamma), coef0, degree, sigma, mmds.data_ptr(),
+                                kid_subset_size, ktype, float(gamma), coef0, degree, sigma, est, mmds.data_ptr(),
                                 stats.data_ptr(), ws.data_ptr(), ws.numel()))
     mean, std = stats.tolist()
     out = {KEY_METRIC_KID_MEAN: float(mean), KEY_METRIC_KID_STD: float(std)}   # kd.py:189-192

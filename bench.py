@@ -26,6 +26,13 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+# The CPU arm must get every host core: torch.distributed.run exports OMP_NUM_THREADS=1 to its
+# workers, and numpy's BLAS reads that once, at import.  Nothing above this line imports numpy or
+# torch, so setting the variables here (reference arm only) is early enough.
+if "reference" in sys.argv[1:]:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 N_REF = int(os.environ.get("AMB_BENCH_N", 200_000))
 N_CAND = int(os.environ.get("AMB_BENCH_M", N_REF))
 DIM = int(os.environ.get("AMB_BENCH_D", 512))
@@ -82,6 +89,17 @@ def cpu_sample_description():
             "materialises N x M fp32 matrices and cannot run 200k (3 x 160 GB)")
 
 
+def blas_threads():
+    """Threads numpy's BLAS will actually use (threadpoolctl), for the cpu_baseline record."""
+    try:
+        import numpy  # noqa: F401  (loads the BLAS that is inspected)
+        from threadpoolctl import threadpool_info
+
+        return max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+    except Exception:
+        return None
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -90,6 +108,12 @@ def run_reference_arm(args):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=cores)      # in case a BLAS was loaded before the environment was fixed
+    except Exception:
+        pass
     ref, cand = cpu_sample_inputs()
     pairs = workload_pairs(CPU_SAMPLE_N, CPU_SAMPLE_N)
     for _ in range(args.warmup):
@@ -104,8 +128,8 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": cpu_sample_description()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "blas_threads": blas_threads(),
+                         "kind": "port", "sample": cpu_sample_description()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -184,14 +208,45 @@ def load_traffic():
     return None
 
 
+def parity_record(result, result_e2e):
+    """Compare this run's result with the committed expectation for the same synthetic inputs
+    (profiles/expected_result.json, written by an N=1 run of this script with AMB_BENCH_WRITE_EXPECTED=1):
+    PRDC fractions must be identical (they are ratios of exact integer counts), FAD and KD agree to
+    1e-9 relative (different reduction orders of the sharded moments / the 100 subset values).  The
+    driver's 1/2/4/8-GPU runs therefore each prove they computed the same answer."""
+    p = ROOT / "profiles" / "expected_result.json"
+    key = f"{N_REF}x{N_CAND}x{DIM}"
+    rec = {"expected_file": str(p.relative_to(ROOT)), "key": key, "e2e_equals_device_resident": result == result_e2e}
+    if os.environ.get("AMB_BENCH_WRITE_EXPECTED"):
+        allv = json.loads(p.read_text()) if p.exists() else {}
+        allv[key] = result
+        p.write_text(json.dumps(allv, indent=1, sort_keys=True))
+    if not p.exists() or key not in json.loads(p.read_text()):
+        rec.update(ok=None, note="no committed expectation for this size")
+        return rec
+    want = json.loads(p.read_text())[key]
+    worst, ok = 0.0, True
+    for k, v in want.items():
+        got = result.get(k)
+        if k in ("precision", "recall", "density", "coverage"):
+            ok = ok and got == v
+        else:
+            rel = abs(got - v) / max(abs(v), 1e-300)
+            worst = max(worst, rel)
+            ok = ok and rel <= 1e-9
+    rec.update(ok=bool(ok), max_rel_fad_kd=worst, prdc_identical=all(result.get(k) == want[k] for k in
+                                                                       ("precision", "recall", "density", "coverage")))
+    return rec
+
+
 def run_b200_arm(args):
     import ctypes as C
 
     import torch
     import torch.distributed as dist
 
-    from audio_metrics_b200 import _lib
-    from audio_metrics_b200.dist import evaluate_sharded, shard_rows
+    from audio_metrics_b200 import AudioMetricsData, _lib
+    from audio_metrics_b200.dist import evaluate_containers, shard_rows
     from audio_metrics_b200.synth import make_sets_torch
 
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -215,9 +270,15 @@ def run_b200_arm(args):
     torch.cuda.empty_cache()
     pairs = workload_pairs(N_REF, N_CAND)
 
-    def step(rs, cs, ready=None):
-        return evaluate_sharded(rs, cs, N_REF, N_CAND, metrics=("fad", "kd", "prdc"), nearest_k=K_NN,
-                                kd_subsets=KD_SUBSETS, kd_subset_size=KD_SUBSET_SIZE, ready=ready)
+    def step(rs, cs, metrics=("fad", "kd", "prdc")):
+        """One pass of the hot path through the public API: fresh containers (nothing cached from
+        the previous step: statistics, packed operands, radii and counts are all recomputed),
+        AudioMetricsData.add, then the fused evaluation AudioMetrics.evaluate runs."""
+        R, Cn = AudioMetricsData(True, dev), AudioMetricsData(True, dev)
+        R.add(rs)
+        Cn.add(cs)
+        return evaluate_containers(R, Cn, metrics, nearest_k=K_NN, kd_subsets=KD_SUBSETS,
+                                   kd_subset_size=KD_SUBSET_SIZE)
 
     def barrier():
         if world > 1:
@@ -254,37 +315,59 @@ def run_b200_arm(args):
     L.amb_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end: pinned host shards -> H2D -> evaluate -> python floats, every step
+    # ---- end to end: pinned host arrays -> AudioMetricsData.add (H2D inside) -> evaluate -> python
+    #      floats, every step.  add() copies on the library's copy stream and returns at once; the
+    #      kernels that read a set wait for its copy on the device, and the evaluation touches the
+    #      candidate only after all reference-only work is queued, so the second copy overlaps the
+    #      first sweep.
     ref_host = ref_shard.cpu().pin_memory()
     cand_host = cand_shard.cpu().pin_memory()
-
-    copy_stream = torch.cuda.Stream(dev)
-
-    def e2e_step():
-        # the two H2D copies run on their own stream; evaluate_sharded queues all reference-only
-        # work behind the first copy and touches the candidate shard only after the second
-        main = torch.cuda.current_stream(dev)
-        copy_stream.wait_stream(main)
-        with torch.cuda.stream(copy_stream):
-            rs = ref_host.to(dev, non_blocking=True)
-            ev_r = torch.cuda.Event(); ev_r.record(copy_stream)
-            cs = cand_host.to(dev, non_blocking=True)
-            ev_c = torch.cuda.Event(); ev_c.record(copy_stream)
-        rs.record_stream(main)
-        cs.record_stream(main)
-        return step(rs, cs, ready=(ev_r, ev_c))
-
-    e2e_step()
-    ms_e2e, result_e2e = timed(e2e_step, max(1, min(args.steps, 3)))
+    step(ref_host, cand_host)
+    ms_e2e, result_e2e = timed(lambda: step(ref_host, cand_host), max(1, min(args.steps, 3)))
     h2d = (ref_host.numel() + cand_host.numel()) * 4
     d2h = 8 * 8 + 8 * KD_SUBSETS   # result scalars + the 100 per-subset MMDs
+
+    # ---- the same metrics through the host-buffer C ABI (amb_host_*: what a ctypes / cgo binding of
+    #      the reference's metric functions calls), rank 0, one GPU: each call stages its own inputs
+    e2e_cabi = None
+    if world == 1 and not args.no_cabi:
+        import numpy as np
+
+        from audio_metrics_b200.dist import kd_subset_indices
+
+        rh, ch = ref_host.numpy(), cand_host.numpy()
+        idx = np.array(kd_subset_indices(N_CAND, N_REF, KD_SUBSET_SIZE, KD_SUBSETS, 1234), copy=True)
+        d = DIM
+
+        def cabi_step():
+            mean_r, cov_r = np.empty(d), np.empty((d, d))
+            mean_c, cov_c = np.empty(d), np.empty((d, d))
+            _lib.check(L.amb_host_stats(local, rh.ctypes.data, 0, N_REF, d, mean_r.ctypes.data, cov_r.ctypes.data))
+            _lib.check(L.amb_host_stats(local, ch.ctypes.data, 0, N_CAND, d, mean_c.ctypes.data, cov_c.ctypes.data))
+            fad = C.c_double()
+            _lib.check(L.amb_host_frechet(local, d, mean_c.ctypes.data, cov_c.ctypes.data, mean_r.ctypes.data,
+                                          cov_r.ctypes.data, C.byref(fad)))
+            kd = (C.c_double * 2)()
+            _lib.check(L.amb_host_kd(local, ch.ctypes.data, N_CAND, rh.ctypes.data, N_REF, d, 0, idx.ctypes.data,
+                                     KD_SUBSETS, KD_SUBSET_SIZE, 1.0 / d, 1.0, 3, None, kd))
+            out = (C.c_double * 4)()
+            _lib.check(L.amb_host_prdc(local, rh.ctypes.data, N_REF, ch.ctypes.data, N_CAND, d, 0, K_NN, out))
+            return {"fad": fad.value, "kernel_distance_mean": kd[0], "kernel_distance_std": kd[1],
+                    "precision": out[0], "recall": out[1], "density": out[2], "coverage": out[3]}
+
+        cabi_step()
+        t0 = time.perf_counter()
+        res_cabi = cabi_step()
+        dt = time.perf_counter() - t0
+        e2e_cabi = {"value": pairs / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": 3 * h2d,
+                    "clock": "host wall clock around five synchronous amb_host_* calls (each stages its own "
+                             "inputs from pageable host memory: 3 x the input bytes cross PCIe)",
+                    "result": res_cabi}
 
     # ---- per-phase latency (FAD latency is part of the headline)
     phases = {}
     for name in ("fad", "kd", "prdc"):
-        fn = lambda name=name: evaluate_sharded(ref_shard, cand_shard, N_REF, N_CAND, metrics=(name,),
-                                                nearest_k=K_NN, kd_subsets=KD_SUBSETS,
-                                                kd_subset_size=KD_SUBSET_SIZE)
+        fn = lambda name=name: step(ref_shard, cand_shard, metrics=(name,))
         fn()
         phases[name + "_ms"], _ = timed(fn, 2)
 
@@ -317,7 +400,8 @@ def run_b200_arm(args):
         cpu_sample_step(ref_s, cand_s)
         dt = time.perf_counter() - t0
         cpu_baseline = {"value": workload_pairs(CPU_SAMPLE_N, CPU_SAMPLE_N) / dt, "unit": UNIT, "cores": cores,
-                        "kind": "port", "sample": cpu_sample_description(), "seconds": dt}
+                        "blas_threads": blas_threads(), "kind": "port", "sample": cpu_sample_description(),
+                        "seconds": dt}
 
     line = {
         "metric": METRIC, "value": pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -327,9 +411,11 @@ def run_b200_arm(args):
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "phases_ms": phases, "result": result,
+        "phases_ms": phases, "result": result, "parity": parity_record(result, result_e2e),
         "pairs_per_step": pairs,
     }
+    if e2e_cabi is not None:
+        line["e2e_c_abi"] = e2e_cabi
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -343,6 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cabi", action="store_true", help="skip the amb_host_* end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -43,6 +43,8 @@ enum {
   AMB_ERR_NUMERIC = -4  /* iteration failed to converge */
 };
 enum { AMB_KERNEL_POLY = 0, AMB_KERNEL_RBF = 1 };
+/* MMD^2 estimators of metrics/kd.py:38-83 (mmd_est); OR in AMB_MMD_UNIT_DIAGONAL for unit_diagonal=True */
+enum { AMB_MMD_UNBIASED = 0, AMB_MMD_BIASED = 1, AMB_MMD_USTAT = 2, AMB_MMD_UNIT_DIAGONAL = 4 };
 
 int amb_version(void);
 const char* amb_last_error(void);
@@ -56,15 +58,27 @@ long long amb_launch_count(void);
 int amb_profile_enable(int on);
 int amb_profile_read(double* out);
 
-/* Process-wide tuning options (names are stable, unknown names return AMB_ERR_ARG):
- *   "jacobi_block"        0 = automatic, 4 / 8 / 16 = columns per block of the Frechet distance's
- *                         block-Jacobi kernel.
- *   "fad_ctas"            0 = automatic, else the most CTAs the Frechet distance's cooperative
- *                         kernels (Cholesky, Jacobi) may use.
- *   "engine_reserve_sms"  SMs the all-pairs sweeps (amb_knn_radii, amb_prdc_counts) leave free.
- * The last two let the N-independent Frechet kernels run on a second stream beside a sweep:
- * the sweep keeps clear of as many SMs as the Frechet kernels are limited to. */
+/* Process-wide diagnostic / tuning options.  They select between implementations that give the
+ * same results (the test-suite holds them to each other) and are meant to be set once, not
+ * toggled around individual calls.  Each option takes its initial value from an environment
+ * variable when the library is first used; after that only amb_set_option changes it — no entry
+ * point reads the environment per call.  Unknown names / out-of-range values: AMB_ERR_ARG.
+ *   "fad_method"          0 polar iteration on fp64 GEMMs (default) | 1 one-sided block Jacobi   AMB_FAD_METHOD
+ *   "fad_factor_eig"      1 = Jacobi eigen-factors instead of pivoted Cholesky                   AMB_FAD_FACTOR=eig
+ *   "jacobi_block"        0 auto | 4 | 8 | 16 columns per block of the block-Jacobi kernel        AMB_JACOBI_BS
+ *   "jacobi_flat"         1 = round-per-grid-barrier Jacobi kernel                               AMB_JACOBI=flat
+ *   "fad_ctas"            0 auto, else the most CTAs the cooperative Frechet kernels may use      AMB_FAD_CTAS
+ *   "fad_debug"           1 = print factor ranks / Jacobi sweeps to stderr (synchronises)         AMB_FAD_DEBUG
+ *   "engine_passes"       0 auto | 3 = three-MMA split-precision sweep for radii / counts         AMB_PASSES
+ *   "engine_cta2"         -1 auto | 0 single-CTA engine | 1 CTA pairs                             AMB_CTA2
+ *   "engine_static"       1 = round-robin work items instead of the dynamic hand-out             AMB_SCHED=static
+ *   "engine_stages", "engine_grid"   B ring depth / persistent CTAs (0 auto)                      AMB_STAGES, AMB_GRID
+ *   "engine_reserve_sms"  SMs the all-pairs sweeps leave free for other streams                   AMB_RESERVE_SMS
+ *   "tail_split", "topk_split", "count_split"   column splits of the sweeps (0 auto)              AMB_TAIL_SPLIT, ...
+ *   "cov_dfma"            1 = FP64-pipe Gram kernel instead of the int8 tensor-core covariance    AMB_COV=dfma
+ *   "debug_single"        engine behind amb_debug_dot_matrix: 0 split | 1 single | 2 CTA pair     AMB_DEBUG_SINGLE */
 int amb_set_option(const char* name, int value);
+int amb_get_option(const char* name);
 
 /* ------------------------------------------------------------------ statistics
  * AudioMetricsData.add / recompute_stats (data.py:37-58): batch mean and unbiased
@@ -89,7 +103,9 @@ int amb_stats_merge(int dev, amb_stream_t stream, int d, long long n1, double* m
  *   |mu_x - mu_y|^2 + tr S_x + tr S_y - 2 sum_i sqrt(lambda_i(S_x S_y)),
  * for `batch` independent pairs.  mu_*: [batch, d], cov_*: [batch, d, d], fp64,
  * out: [batch] fp64.  The eigenvalue sum is evaluated as the nuclear norm of
- * F_y^T F_x with S = F F^T (one-sided Jacobi, fp64). */
+ * M = F_y^T F_x with S = F F^T (pivoted Cholesky factors): tr(U^T M) with U the polar
+ * factor of M from an inverse-free polynomial iteration on fp64 GEMMs (or, option
+ * "fad_method" = 1, the sum of the singular values from one-sided Jacobi). */
 size_t amb_frechet_ws_bytes(int batch, int d);
 int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu_x,
                 const double* cov_x, const double* mu_y, const double* cov_y, double* out, void* ws,
@@ -109,12 +125,16 @@ int amb_pack(int dev, amb_stream_t stream, const void* X, int dtype, long long n
  * mmd2 (kd.py:38-83).  F1 [n1,d], F2 [n2,d]; idx [S,2,m] int32 holds, per subset,
  * the m row indices drawn from F1 then the m drawn from F2 (the host draws them
  * with numpy's default_rng exactly as kd.py:176,185-186 does).
+ * mmd_est selects the estimator of kd.py:38-83: AMB_MMD_UNBIASED is what kernel_mmd2
+ * (kd.py:119-124) hard-codes; "biased" and "u-statistic" are only reachable by calling
+ * mmd2() directly in the reference.
  * mmd2_out [S] fp64; stats_out[2] = {mean, population std} (kd.py:189-192). */
 size_t amb_kd_ws_bytes(int S, int m, int d);
 int amb_kd_subsets(int dev, amb_stream_t stream, const void* F1, long long n1, long long ld1,
                    const void* F2, long long n2, long long ld2, int d, int dtype, const int32_t* idx,
                    int S, int m, int kernel_type, double gamma, double coef0, int degree,
-                   double sigma, double* mmd2_out, double* stats_out, void* ws, size_t ws_bytes);
+                   double sigma, int mmd_est, double* mmd2_out, double* stats_out, void* ws,
+                   size_t ws_bytes);
 
 /* --------------------------------------------------------------------------- PRDC
  * Both PRDC entry points use the tensor-core sweep as a filter with a proven
@@ -125,12 +145,16 @@ int amb_kd_subsets(int dev, amb_stream_t stream, const void* F1, long long n1, l
  * smallest Euclidean distance from row i to all rows of the set (self
  * included), returned as the correctly rounded fp32 value of the exact distance.
  * Computes radii for rows [row0, row0+nrows) of the set (row0 % 128 == 0; shards that
- * start on an even tile, row0 % 256 == 0, run on the CTA-pair kernel) against all n rows.  radii: [nrows] fp32.  1 <= k <= 29 and k+1 <= n (the
- * reference's kthvalue raises for k+1 > n). */
+ * start on an even tile, row0 % 256 == 0, run on the CTA-pair kernel) against all n rows.
+ * radii: [nrows] fp32.  1 <= k <= 29 and k+1 <= n (the reference's kthvalue raises for
+ * k+1 > n).  nrows == 0 is a no-op for any row0 (empty row shard).
+ * Rows whose answer the tensor-core filter cannot certify (near-ties beyond the kept margin,
+ * duplicated or collinear rows) are ALL resolved by an exhaustive exact scan; their number
+ * is written to n_exhaustive (device int64, nullable) — a cost indicator, not an error. */
 size_t amb_knn_ws_bytes(long long nrows, long long n, int d, int k);
 int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long long ld,
                   const void* packed, long long n, int d, long long row0, long long nrows, int k,
-                  float* radii, void* ws, size_t ws_bytes);
+                  float* radii, long long* n_exhaustive, void* ws, size_t ws_bytes);
 
 /* prdc (metrics/prdc.py:18-50) neighbourhood counts for reference rows
  * [row0, row0+nrows) (row0 % 128 == 0) against all m candidates, strict '<' on
@@ -140,11 +164,24 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
  *   row_cover[i]   = any_j  D_ij < r_ref[i]   (== min_j D_ij < r_ref[i], prdc.py:48)
  * r_ref: [n_ref] fp32 (indexed by absolute row), r_cand: [m] fp32.
  * col_count [m] int32 is accumulated and must be zeroed by the caller before the
- * first shard; row_recall / row_cover [nrows] are overwritten.  n_uncertain
- * (device int64, nullable) receives the number of pairs that fell inside the
- * band; if it exceeds amb_prdc_list_cap(n_ref, m) the excess pairs were NOT
- * re-decided and the caller must treat the result as invalid. */
+ * first shard; row_recall / row_cover [nrows] are overwritten.  nrows == 0 is a no-op for
+ * any row0 (empty row shard).
+ *
+ * Pairs inside the band go through a refine list that lives in the workspace: its capacity
+ * is whatever `ws_bytes` holds beyond the fixed part (amb_prdc_ws_list_cap).  n_uncertain
+ * (device int64, nullable) receives the number of such pairs; if it exceeds the capacity
+ * the excess pairs were NOT re-decided, the outputs of this call are invalid, and the
+ * caller repeats the call (after re-zeroing what it accumulated into col_count) with a
+ * workspace of amb_prdc_ws_bytes_cap(n_ref, m, n_uncertain) bytes — the number of pairs in
+ * the band does not depend on the capacity — or, if that much memory cannot be had, calls
+ * amb_prdc_counts_exact, which needs no list.  amb_host_prdc and the Python binding do
+ * exactly that, so no input makes them fail where prdc.py:18-50 returns.
+ *   amb_prdc_ws_bytes       workspace with the default capacity amb_prdc_list_cap(n_ref, m)
+ *   amb_prdc_ws_bytes_cap   workspace for a given capacity
+ *   amb_prdc_ws_list_cap    capacity a workspace of ws_bytes provides */
 size_t amb_prdc_ws_bytes(long long n_ref, long long m);
+size_t amb_prdc_ws_bytes_cap(long long n_ref, long long m, long long list_cap);
+long long amb_prdc_ws_list_cap(long long n_ref, long long m, size_t ws_bytes);
 long long amb_prdc_list_cap(long long n_ref, long long m);
 int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr,
                     const void* packed_ref, long long n_ref, const float* r_ref, const void* C,
@@ -152,6 +189,13 @@ int amb_prdc_counts(int dev, amb_stream_t stream, const void* R, long long ldr,
                     int dtype, long long row0, long long nrows, int32_t* col_count,
                     uint8_t* row_recall, uint8_t* row_cover, long long* n_uncertain, void* ws,
                     size_t ws_bytes);
+/* The same outputs from an exhaustive fp64 evaluation of every (row, candidate) pair on the
+ * CUDA cores: no packed operands, no workspace, no list, n_ref * m * d operations.  The last
+ * rung of the overflow ladder described above; also a cross-check for the filtered path. */
+int amb_prdc_counts_exact(int dev, amb_stream_t stream, const void* R, long long ldr, long long n_ref,
+                          const float* r_ref, const void* C, long long ldc, long long m,
+                          const float* r_cand, int d, int dtype, long long row0, long long nrows,
+                          int32_t* col_count, uint8_t* row_recall, uint8_t* row_cover);
 /* totals[4] (int64) += { #cols with count>0, sum of col_count, #rows recalled,
  * #rows covered } — the numerators of precision, density*k, recall, coverage.
  * Null array arguments are skipped. */

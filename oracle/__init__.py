@@ -21,6 +21,6 @@ restatements below follow the published algorithms of ``torch.cov``,
 """
 from .stats import batch_stats, chan_merge, StreamingStats  # noqa: F401
 from .fad import frechet_from_stats, frechet_sqrtm  # noqa: F401
-from .kd import kernel_distance, draw_subset_indices, mmd2_unbiased, polynomial_kernel, kd_subset_size  # noqa: F401
+from .kd import kernel_distance, draw_subset_indices, mmd2, mmd2_unbiased, polynomial_kernel, kd_subset_size  # noqa: F401
 from .prdc import cdist_mm, nearest_neighbour_distances, prdc, prdc_counts, prdc_counts_chunked, prdc_bracket  # noqa: F401
 from .apa import apa, apa_from_fads  # noqa: F401

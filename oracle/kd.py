@@ -38,6 +38,29 @@ def mmd2_unbiased(K_XX, K_XY, K_YY):
     return mmd2
 
 
+def mmd2(K_XX, K_XY, K_YY, unit_diagonal=False, mmd_est="unbiased"):
+    """kd.py:38-83 with all three estimators ("biased" and "u-statistic" are only reachable by
+    calling mmd2 directly in the reference; kernel_mmd2, kd.py:119-124, hard-codes "unbiased")."""
+    assert mmd_est in ("biased", "unbiased", "u-statistic"), "Invalid value of mmd_est"   # kd.py:39-43
+    m = K_XX.shape[0]
+    assert K_XX.shape == (m, m) and K_XY.shape == (m, m) and K_YY.shape == (m, m)          # kd.py:45-48
+    if unit_diagonal:                                   # kd.py:52-54
+        diag_X = diag_Y = 1
+        sum_diag_X = sum_diag_Y = m
+    else:                                               # kd.py:55-60
+        diag_X, diag_Y = np.diagonal(K_XX), np.diagonal(K_YY)
+        sum_diag_X, sum_diag_Y = diag_X.sum(), diag_Y.sum()
+    Kt_XX_sum = (K_XX.sum(axis=1) - diag_X).sum()       # kd.py:62,66
+    Kt_YY_sum = (K_YY.sum(axis=1) - diag_Y).sum()       # kd.py:63,67
+    K_XY_sum = K_XY.sum(axis=0).sum()                   # kd.py:64,68
+    if mmd_est == "biased":                             # kd.py:70-75
+        return (Kt_XX_sum + sum_diag_X) / (m * m) + (Kt_YY_sum + sum_diag_Y) / (m * m) - 2 * K_XY_sum / (m * m)
+    out = (Kt_XX_sum + Kt_YY_sum) / (m * (m - 1))       # kd.py:77
+    if mmd_est == "unbiased":
+        return out - 2 * K_XY_sum / (m * m)             # kd.py:79
+    return out - 2 * (K_XY_sum - np.trace(K_XY)) / (m * (m - 1))   # kd.py:81
+
+
 def kd_subset_size(n1, n2, kid_subset_size=KID_SUBSET_SIZE):
     """kd.py:157-168: if subset_size >= min(n1, n2) it becomes max(1, min // 2)."""
     n = min(n1, n2)
@@ -59,7 +82,8 @@ def draw_subset_indices(n1, n2, m, subsets=KID_SUBSETS, seed=RNG_SEED):
 
 def kernel_distance(f1, f2, subsets=KID_SUBSETS, subset_size=KID_SUBSET_SIZE, seed=RNG_SEED,
                     degree=KID_DEGREE, gamma=None, coef0=KID_COEF0, compute_dtype=None,
-                    return_mmds=False, kernel_type="polynomial", sigma=10.0):
+                    return_mmds=False, kernel_type="polynomial", sigma=10.0, mmd_est="unbiased",
+                    unit_diagonal=False):
     """kd.py:127-194 kid_features_to_metric with the polynomial kernel (or, kernel_type="rbf",
     the RBF kernel of kd.py:86-109 that only the keyword interface reaches).
 
@@ -88,7 +112,10 @@ def kernel_distance(f1, f2, subsets=KID_SUBSETS, subset_size=KID_SUBSET_SIZE, se
             k11 = polynomial_kernel(a, a, degree, gamma, coef0)   # kd.py:120
             k22 = polynomial_kernel(b, b, degree, gamma, coef0)   # kd.py:121
             k12 = polynomial_kernel(a, b, degree, gamma, coef0)   # kd.py:122
-        mmds[i] = mmd2_unbiased(k11, k12, k22)                # kd.py:124
+        if mmd_est == "unbiased" and not unit_diagonal:
+            mmds[i] = mmd2_unbiased(k11, k12, k22)            # kd.py:124
+        else:
+            mmds[i] = mmd2(k11, k12, k22, unit_diagonal=unit_diagonal, mmd_est=mmd_est)
     out = {"kernel_distance_mean": float(np.mean(mmds)), "kernel_distance_std": float(np.std(mmds))}
     if return_mmds:
         out["mmds"] = mmds

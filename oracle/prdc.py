@@ -37,6 +37,19 @@ def cdist_exact(x1, x2) -> np.ndarray:
     return np.sqrt(np.maximum(d2, 0))
 
 
+def cdist_diff(x1, x2, chunk=64) -> np.ndarray:
+    """Distances in the difference form sqrt(sum (x - y)^2), fp64: no cancellation, so duplicated
+    rows are at distance exactly 0 (cdist_exact's |x|^2 + |y|^2 - 2 x.y leaves 1e-8 of noise there).
+    O(n m d) memory traffic — for the small duplicate / tie cases only."""
+    x1 = np.asarray(x1, dtype=np.float64)
+    x2 = np.asarray(x2, dtype=np.float64)
+    out = np.empty((len(x1), len(x2)))
+    for s in range(0, len(x1), chunk):
+        diff = x1[s:s + chunk, None, :] - x2[None, :, :]
+        out[s:s + chunk] = np.sqrt(np.einsum("ijk,ijk->ij", diff, diff))
+    return out
+
+
 def nearest_neighbour_distances(x, nearest_k, dist=cdist_mm):
     """prdc.py:4-14: kthvalue(cdist(x, x), k + 1) per row (self-distance included)."""
     x = np.asarray(x)
@@ -121,16 +134,15 @@ def prdc_bracket(ref, cand, nearest_k, eps, chunk=4096):
         return out
 
     r_ref, r_cand = radii(ref64), radii(cand64)
-    res = []
-    for f in (1.0 - eps, 1.0 + eps):
-        col = np.zeros(len(cand64), dtype=np.int64)
-        rec = np.zeros(len(ref64), dtype=bool)
-        cov = np.zeros(len(ref64), dtype=bool)
-        for s in range(0, len(ref64), chunk):
+    fs = (1.0 - eps, 1.0 + eps)
+    res = [dict(col_count=np.zeros(len(cand64), dtype=np.int64), recall_rows=np.zeros(len(ref64), dtype=bool),
+                cover_rows=np.zeros(len(ref64), dtype=bool)) for _ in fs]
+    for s in range(0, len(ref64), chunk):
+        D = cdist_exact(ref64[s:s + chunk], cand64)
+        for f, out in zip(fs, res):
             # widen/narrow the comparison itself so distance error is covered too
-            D = cdist_exact(ref64[s:s + chunk], cand64)
-            col += (D < f * r_ref[s:s + chunk, None]).sum(axis=0)
-            rec[s:s + chunk] = (D < f * r_cand[None, :]).any(axis=1)
-            cov[s:s + chunk] = (D < f * r_ref[s:s + chunk, None]).any(axis=1)
-        res.append(dict(col_count=col, recall_rows=rec, cover_rows=cov))
+            in_ref = D < f * r_ref[s:s + chunk, None]
+            out["col_count"] += in_ref.sum(axis=0)
+            out["recall_rows"][s:s + chunk] = (D < f * r_cand[None, :]).any(axis=1)
+            out["cover_rows"][s:s + chunk] = in_ref.any(axis=1)
     return res[0], res[1], r_ref, r_cand

@@ -36,7 +36,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n_ref, n_cand, d, k, out):
+def _worker(rank, world, port, n_ref, n_cand, d, k, out, overflow=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -45,22 +45,31 @@ def _worker(rank, world, port, n_ref, n_cand, d, k, out):
         ref, cand = make_sets_numpy(n_ref, n_cand, d, seed=77)
         r0, rn, _ = shard_rows(n_ref, world, rank)
         c0, cn, _ = shard_rows(n_cand, world, rank)
+        ops = OracleOps()
+        ops.overflow_once = overflow
         res = evaluate_sharded(torch.from_numpy(ref[r0:r0 + rn]), torch.from_numpy(cand[c0:c0 + cn]), n_ref, n_cand,
-                               nearest_k=k, ops=OracleOps(), kd_subsets=7, kd_subset_size=60)
+                               nearest_k=k, ops=ops, kd_subsets=7, kd_subset_size=60)
         out[rank] = res
+        out[f"calls{rank}"] = list(ops.calls)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_ref,n_cand", [(300, 200), (130, 257)])
-def test_sharded_equals_single_process(n_ref, n_cand):
+@pytest.mark.parametrize("n_ref,n_cand,overflow", [(300, 200, False), (130, 257, False), (600, 300, True)])
+def test_sharded_equals_single_process(n_ref, n_cand, overflow):
     import sys
     sys.path.insert(0, os.path.dirname(__file__))
     d, k, world = 32, 4, 2
     mgr = mp.Manager()
     out = mgr.dict()
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, n_ref, n_cand, d, k, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n_ref, n_cand, d, k, out, overflow), nprocs=world, join=True)
+    if overflow:
+        # rank 0's refine list "overflowed" (more near-ties than capacity) while rank 1's did not: the
+        # MAX-reduced count makes BOTH ranks repeat the count sweep with a list of the reported size
+        assert out["calls0"] == out["calls1"] == [None, (1 << 20) + 5]
+    else:
+        assert out["calls0"] == out["calls1"] == [None]
     ref, cand = make_sets_numpy(n_ref, n_cand, d, seed=77)
     assert out[0] == out[1]
     res = out[0]

@@ -18,7 +18,11 @@ def _amd(x, store=True):
 
 
 @pytest.mark.parametrize("name", SET_CASES)
-def test_cuda_path_matches_reference_golden(cuda_device, name):
+def test_cuda_path_matches_reference_golden_kd_at_reference_fp32_noise(cuda_device, name):
+    """FAD 1e-5, PRDC exact up to attributed ties, radii 2e-4 (reference fp32), and KD at 5e-3: the
+    golden KD values are the reference's own fp32 evaluation, whose distance from an fp64 evaluation
+    of the same subsets is 6e-4 ... 3 %; the north-star 1e-4 is held against fp64 in
+    test_gpu_parity.py::test_kd_matches_oracle and test_kd_keyword_variants_match_reference."""
     ref, cand, g = case_inputs(name)
     a = arrays()
     k, n, m = g["k"], len(ref), len(cand)
@@ -33,11 +37,23 @@ def test_cuda_path_matches_reference_golden(cuda_device, name):
     np.testing.assert_allclose(R.get_radii(k).cpu().numpy(), a[f"{name}/r_ref"], rtol=2e-4, atol=2e-6)
     np.testing.assert_allclose(C.get_radii(k).cpu().numpy(), a[f"{name}/r_cand"], rtol=2e-4, atol=2e-6)
     col, rec, cov, _ = prdc_totals(R, C, k)
-    assert np.abs(col.cpu().numpy() - a[f"{name}/col_count"]).sum() <= 4
-    assert (rec.cpu().numpy().astype(bool) != unpack_rows(a[f"{name}/recall_rows"], n)).sum() <= 2
-    assert (cov.cpu().numpy().astype(bool) != unpack_rows(a[f"{name}/cover_rows"], n)).sum() <= 2
+    col, rec, cov = col.cpu().numpy(), rec.cpu().numpy().astype(bool), cov.cpu().numpy().astype(bool)
+    col_ref = a[f"{name}/col_count"]
+    rec_ref, cov_ref = unpack_rows(a[f"{name}/recall_rows"], n), unpack_rows(a[f"{name}/cover_rows"], n)
+    # north_star: counts match the reference exactly, except for ties within eps of a radius.  Ours are
+    # the exact-arithmetic counts; wherever they differ from the reference's, the pair responsible must
+    # lie within the reference's own fp32 cdist error of the radius it is compared with — attribute
+    # every difference to such a pair (and there may be only a handful).
+    if (col != col_ref).any() or (rec != rec_ref).any() or (cov != cov_ref).any():
+        import oracle
+        from test_gpu_robustness import _attribute_differences
+        from oracle.prdc import cdist_exact
+        r_ref64 = np.concatenate([np.partition(cdist_exact(ref[s:s + 2048], ref), k, axis=-1)[:, k] for s in range(0, n, 2048)])
+        r_cand64 = np.concatenate([np.partition(cdist_exact(cand[s:s + 2048], cand), k, axis=-1)[:, k] for s in range(0, m, 2048)])
+        n_diff = _attribute_differences(ref, cand, col, rec, cov, col_ref, rec_ref, cov_ref, r_ref64, r_cand64)
+        assert n_diff <= 8
     out = prdc(R, C, k)
-    for key, tol in (("precision", 3 / m), ("recall", 3 / n), ("density", 6 / (k * m)), ("coverage", 3 / n)):
+    for key, tol in (("precision", 3 / m), ("recall", 3 / n), ("density", 6 / (k * m)), ("coverage", 3 / n)):   # implied by the attribution above
         assert abs(out[key] - g[f"prdc_{key}"]) <= tol, (key, out[key], g[f"prdc_{key}"])
 
 
@@ -91,3 +107,33 @@ def test_kd_keyword_variants_match_reference(cuda_device):
             want64, want32 = v["reference_f64"][key], v["reference_f32"][key]
             assert got[key] == pytest.approx(want64, rel=1e-4, abs=1e-9), (name, key)      # north-star tolerance
             assert abs(got[key] - want32) <= 2 * abs(want32 - want64) + 1e-4 * abs(want64) + 1e-9, (name, key)
+
+
+def test_kd_estimators_match_reference(cuda_device):
+    """kd.py:38-83 "biased" / "u-statistic" / unit_diagonal through the fused kernel (the reference only
+    reaches them through mmd2 itself), per subset, against the unmodified reference's values."""
+    import json
+    from pathlib import Path
+
+    from audio_metrics_b200.metrics.kd import kid_features_to_metric, mmd2
+    from audio_metrics_b200.synth import make_sets_numpy
+
+    g = json.loads((Path(__file__).parent / "golden" / "golden_kd_estimators.json").read_text())
+    i = g["input"]
+    ref, cand = make_sets_numpy(i["n_ref"], i["n_cand"], i["d"], seed=i["seed"])
+    for name, v in g["variants"].items():
+        kw = dict(v["kwargs"], kid_subsets=g["subsets"], kid_subset_size=g["subset_size"], rng_seed=g["seed"],
+                  return_mmds=True)
+        got = kid_features_to_metric(torch.from_numpy(cand), torch.from_numpy(ref), **kw)
+        np.testing.assert_allclose(got["mmds"], v["reference_f64"]["mmds"], rtol=1e-4, atol=1e-9, err_msg=name)
+        for key in ("kernel_distance_mean", "kernel_distance_std"):
+            assert got[key] == pytest.approx(v["reference_f64"][key], rel=1e-4, abs=1e-9), (name, key)
+    # mmd2 on explicit kernel matrices (what the reference's signature takes)
+    import oracle
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal((50, 16)), rng.standard_normal((50, 16)) + 0.2
+    kxx, kxy, kyy = (oracle.polynomial_kernel(a, b) for a, b in ((x, x), (x, y), (y, y)))
+    for est in ("biased", "unbiased", "u-statistic"):
+        for unit in (False, True):
+            assert mmd2(kxx, kxy, kyy, unit_diagonal=unit, mmd_est=est) == pytest.approx(
+                oracle.mmd2(kxx, kxy, kyy, unit_diagonal=unit, mmd_est=est), rel=1e-12, abs=1e-15)

@@ -15,6 +15,7 @@ import torch
 import oracle
 from oracle.prdc import cdist_exact
 from audio_metrics_b200 import AudioMetricsData, frechet_distance, prdc
+from audio_metrics_b200._lib import options
 from audio_metrics_b200.metrics.prdc import nearest_neighbour_distances, prdc_totals
 from audio_metrics_b200.synth import make_sets_numpy, make_sets_torch
 
@@ -34,18 +35,16 @@ def _stats64(x):
 
 # ------------------------------------------------------------------ engine variants
 @pytest.mark.parametrize("n,m,d,k", [(3000, 2600, 512, 5), (1500, 1500, 96, 10), (2000, 1000, 300, 2)])
-def test_single_pass_and_split_sweeps_agree(cuda_device, monkeypatch, n, m, d, k):
+def test_single_pass_and_split_sweeps_agree(cuda_device, n, m, d, k):
     ref, cand = make_sets_numpy(n, m, d, seed=n + d + k)
     out = {}
-    for name, passes, cta2, sched in (("pair", "1", "1", "dynamic"), ("pair_static", "1", "1", "static"),
-                                      ("single", "1", "0", "dynamic"), ("split", "3", "0", "dynamic")):
-        monkeypatch.setenv("AMB_PASSES", passes)
-        monkeypatch.setenv("AMB_CTA2", cta2)
-        monkeypatch.setenv("AMB_SCHED", sched)
-        R, C = _amd(ref), _amd(cand)
-        r_ref = nearest_neighbour_distances(R, k)
-        col, rec, cov, tot = prdc_totals(R, C, k)
-        out[name] = (r_ref.cpu().numpy(), col.cpu().numpy(), rec.cpu().numpy(), cov.cpu().numpy(), int(tot[4]))
+    for name, passes, cta2, static in (("pair", 0, 1, 0), ("pair_static", 0, 1, 1), ("single", 0, 0, 0),
+                                       ("split", 3, 0, 0)):
+        with options(engine_passes=passes, engine_cta2=cta2, engine_static=static):
+            R, C = _amd(ref), _amd(cand)
+            r_ref = nearest_neighbour_distances(R, k)
+            col, rec, cov, tot = prdc_totals(R, C, k)
+            out[name] = (r_ref.cpu().numpy(), col.cpu().numpy(), rec.cpu().numpy(), cov.cpu().numpy(), int(tot[4]))
     for other in ("pair_static", "single", "split"):
         for a, b in zip(out["pair"][:4], out[other][:4]):
             assert np.array_equal(a, b)
@@ -114,12 +113,13 @@ def test_tensor_core_covariance_stress(cuda_device):
     np.testing.assert_allclose(cov[8:, 8:], c_ref[8:, 8:], rtol=1e-8, atol=1e-10)
 
 
-def test_covariance_paths_agree_and_stream(cuda_device, monkeypatch):
+def test_covariance_paths_agree_and_stream(cuda_device):
     ref, _ = make_sets_numpy(10000, 8, 512, seed=2)
     tc = _amd(ref, store=False)
-    monkeypatch.setenv("AMB_COV", "dfma")
-    fp = _amd(ref, store=False)
-    monkeypatch.delenv("AMB_COV")
+    tc.cov
+    with options(cov_dfma=1):
+        fp = _amd(ref, store=False)
+        fp.cov                      # statistics are folded in when read: read them under the option
     np.testing.assert_allclose(tc.cov.cpu().numpy(), fp.cov.cpu().numpy(), rtol=1e-8, atol=1e-13)
     np.testing.assert_allclose(tc.mean.cpu().numpy(), fp.mean.cpu().numpy(), rtol=0, atol=2.0 ** -30)
     # two tensor-core blocks merged by Chan's update == one block (reference tests/test_data.py:6-31)
@@ -129,50 +129,87 @@ def test_covariance_paths_agree_and_stream(cuda_device, monkeypatch):
 
 
 # -------------------------------------------------------------------- Frechet paths
-def test_frechet_factor_paths_agree(cuda_device, monkeypatch):
+def test_frechet_factor_paths_agree(cuda_device):
+    """Polar iteration (default) vs one-sided Jacobi, pivoted-Cholesky factors vs Jacobi eigen-factors,
+    on singular covariances with n >> d."""
     ref, cand = make_sets_numpy(6000, 5000, 200, seed=4)
     ref[:, 10] = ref[:, 11]                          # singular covariances with n >> d
     cand[:, 10] = cand[:, 11]
     ref[:, 12] = 0.0
     A, B = _amd(cand, False), _amd(ref, False)
-    chol = frechet_distance(A, B)
-    monkeypatch.setenv("AMB_FAD_FACTOR", "eig")
-    eig = frechet_distance(A, B)
-    monkeypatch.delenv("AMB_FAD_FACTOR")
+    polar = frechet_distance(A, B)
+    with options(fad_method=1):
+        chol = frechet_distance(A, B)
+        with options(fad_factor_eig=1):
+            eig = frechet_distance(A, B)
+        for bs in (16, 8, 4):                        # Jacobi block sizes
+            with options(jacobi_block=bs):
+                assert frechet_distance(A, B) == pytest.approx(chol, rel=1e-10)
     mx, cx = _stats64(cand); my, cy = _stats64(ref)
     want = oracle.frechet_from_stats(mx, cx, my, cy)
+    assert polar == pytest.approx(want, rel=1e-5)
     assert chol == pytest.approx(want, rel=1e-5)
     assert eig == pytest.approx(want, rel=1e-5)
     assert chol == pytest.approx(eig, rel=1e-7)
-    for bs in ("16", "8", "4"):                      # Jacobi block sizes
-        monkeypatch.setenv("AMB_JACOBI_BS", bs)
-        assert frechet_distance(A, B) == pytest.approx(chol, rel=1e-10)
+    assert polar == pytest.approx(chol, rel=1e-9)    # two algorithms for the same nuclear norm
 
 
-def test_options_and_shared_gpu_step(cuda_device):
-    """amb_set_option, and the overlapped step (FAD on a side stream beside a narrowed sweep) against
-    the plain sequential calls."""
+@pytest.mark.parametrize("case", ["full_rank_d512", "n_lt_d", "rank1", "scaled_columns", "identical", "d33"])
+def test_frechet_polar_matches_jacobi_and_svd(cuda_device, case):
+    """The GEMM-only polar iteration against the Jacobi path and an fp64 SVD of the same factors'
+    product, on the inputs that break naive square-root iterations."""
+    rng = np.random.default_rng(7)
+    if case == "full_rank_d512":
+        ref, cand = make_sets_numpy(3000, 2500, 512, seed=1)
+    elif case == "n_lt_d":
+        ref, cand = make_sets_numpy(100, 90, 128, seed=12)
+    elif case == "rank1":
+        ref = np.outer(rng.random(100) * 300, np.arange(10.0)); cand = np.outer(rng.random(100) * 300, np.arange(10.0))
+    elif case == "scaled_columns":
+        ref, cand = make_sets_numpy(3000, 2500, 256, seed=3)
+        sc = np.geomspace(1e-6, 1e6, 256)
+        ref, cand = ref * sc, cand * sc               # float64, condition ~1e13 after the factor product
+    elif case == "identical":
+        ref, _ = make_sets_numpy(2000, 8, 200, seed=5); cand = ref.copy()
+    else:
+        ref, cand = make_sets_numpy(500, 400, 33, seed=9)
+    A, B = _amd(cand, False), _amd(ref, False)
+    polar = frechet_distance(A, B)
+    with options(fad_method=1):
+        jac = frechet_distance(A, B)
+    mx, cx = _stats64(cand); my, cy = _stats64(ref)
+    scale = np.trace(cx) + np.trace(cy)
+    assert abs(polar - jac) <= 1e-10 * scale
+    want = oracle.frechet_from_stats(mx, cx, my, cy)
+    assert abs(polar - want) <= 1e-5 * abs(want) + 1e-9 * scale
+
+
+def test_options_and_fused_step(cuda_device):
+    """amb_set_option / amb_get_option, and the fused step (one read-back) against the plain
+    sequential calls."""
     from audio_metrics_b200 import _lib, kernel_distance
-    from audio_metrics_b200.dist import evaluate_sharded
+    from audio_metrics_b200.dist import evaluate_containers, evaluate_sharded
     L = _lib.lib()
     assert L.amb_set_option(b"no_such_option", 1) == _lib.AMB_ERR_ARG
     assert L.amb_set_option(b"jacobi_block", 5) == _lib.AMB_ERR_ARG
     for name in (b"jacobi_block", b"fad_ctas", b"engine_reserve_sms"):
-        assert L.amb_set_option(name, 16) == 0 and L.amb_set_option(name, 0) == 0
+        assert L.amb_set_option(name, 16) == 0 and L.amb_get_option(name) == 16 and L.amb_set_option(name, 0) == 0
+    with options(engine_passes=3):
+        assert L.amb_get_option(b"engine_passes") == 3
+    assert L.amb_get_option(b"engine_passes") == 0
     ref, cand = make_sets_numpy(6000, 5200, 512, seed=17)
     R, C = _amd(ref), _amd(cand)
     want = dict(fad=frechet_distance(C, R), **kernel_distance(C, R), **prdc(R, C, 5))
     got = evaluate_sharded(torch.from_numpy(ref).cuda(), torch.from_numpy(cand).cuda(), 6000, 5200, nearest_k=5)
-    assert got["fad"] == pytest.approx(want["fad"], rel=1e-9)
-    for key in ("kernel_distance_mean", "kernel_distance_std"):      # host numpy vs device reduction of the same 100 values
-        assert got[key] == pytest.approx(want[key], rel=1e-12), key
-    for key in ("precision", "recall", "density", "coverage"):
-        assert got[key] == want[key], key
-    L.amb_set_option(b"engine_reserve_sms", 100)       # a very narrow sweep gives the same counts
-    try:
+    got2 = evaluate_containers(_amd(ref), _amd(cand), nearest_k=5)
+    for g in (got, got2):
+        assert g["fad"] == pytest.approx(want["fad"], rel=1e-9)
+        for key in ("kernel_distance_mean", "kernel_distance_std"):  # host numpy vs device reduction of the same 100 values
+            assert g[key] == pytest.approx(want[key], rel=1e-12), key
+        for key in ("precision", "recall", "density", "coverage"):
+            assert g[key] == want[key], key
+    with options(engine_reserve_sms=100):              # a very narrow sweep gives the same counts
         assert prdc(_amd(ref), _amd(cand), 5) == {k: want[k] for k in ("precision", "recall", "density", "coverage")}
-    finally:
-        L.amb_set_option(b"engine_reserve_sms", 0)
 
 
 # ------------------------------------------------------- full-size properties (BASELINE N)

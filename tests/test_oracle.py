@@ -146,3 +146,25 @@ def test_kd_keyword_variants_match_reference_goldens():
         got32 = oracle.kernel_distance(cand, ref, **args)
         for key in ("kernel_distance_mean", "kernel_distance_std"):
             assert got32[key] == pytest.approx(v["reference_f32"][key], rel=5e-3, abs=2e-8), (name, key)
+
+
+def test_mmd2_estimators_match_reference_goldens():
+    """kd.py:38-83 "biased" / "u-statistic" / unit_diagonal: the oracle against values produced by the
+    unmodified reference's own mmd2 (tests/golden/make_golden_kd_estimators.py)."""
+    import json
+    from pathlib import Path
+
+    from audio_metrics_b200.synth import make_sets_numpy
+
+    g = json.loads((Path(__file__).parent / "golden" / "golden_kd_estimators.json").read_text())
+    i = g["input"]
+    ref, cand = make_sets_numpy(i["n_ref"], i["n_cand"], i["d"], seed=i["seed"])
+    for name, v in g["variants"].items():
+        kw = v["kwargs"]
+        args = dict(subsets=g["subsets"], subset_size=g["subset_size"], seed=g["seed"],
+                    kernel_type=kw.get("kernel_type", "polynomial"), sigma=kw.get("kid_sigma", 10.0),
+                    mmd_est=kw["mmd_est"], unit_diagonal=kw.get("unit_diagonal", False), return_mmds=True)
+        got64 = oracle.kernel_distance(cand, ref, compute_dtype=np.float64, **args)
+        np.testing.assert_allclose(got64["mmds"], v["reference_f64"]["mmds"], rtol=1e-9, atol=1e-15)
+        got32 = oracle.kernel_distance(cand, ref, **args)
+        np.testing.assert_allclose(got32["mmds"], v["reference_f32"]["mmds"], rtol=5e-3, atol=2e-7)
