@@ -35,6 +35,9 @@ SIGNATURES = {
     "amb_stats_merge": (_i, [_i, _vp, _i, _ll, _vp, _vp, _ll, _vp, _vp, _vp]),
     "amb_frechet_ws_bytes": (_sz, [_i, _i]),
     "amb_frechet": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
+    "amb_sym_eig_ws_bytes": (_sz, [_i]),
+    "amb_sym_eig": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp, _sz]),
+    "amb_pca_transform": (_i, [_i, _vp, _vp, _i, _ll, _i, _ll, _vp, _vp, _i, _vp]),
     "amb_packed_bytes": (_sz, [_ll, _i]),
     "amb_pack": (_i, [_i, _vp, _vp, _i, _ll, _i, _ll, _vp]),
     "amb_kd_ws_bytes": (_sz, [_i, _i, _i]),

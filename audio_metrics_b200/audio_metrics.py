@@ -30,8 +30,8 @@ class AudioMetrics:
         self.need_apa = "apa" in self.metrics
         self.win_dur = win_dur
         self.input_sr = input_sr
-        self.stem_projection = None if n_pca is None else IncrementalPCA(n_components=n_pca)
-        self.mix_projection = None if n_pca is None else IncrementalPCA(n_components=n_pca)
+        self.stem_projection = None if n_pca is None else IncrementalPCA(n_components=n_pca, device=self.device)
+        self.mix_projection = None if n_pca is None else IncrementalPCA(n_components=n_pca, device=self.device)
         self.embedder = self.get_embedder(embedder) if embedder is None or isinstance(embedder, str) else embedder
         self.mix_function = (self.get_mix_function(mix_function)
                              if mix_function is None or isinstance(mix_function, str) else mix_function)
@@ -132,7 +132,7 @@ class AudioMetrics:
             return ref, cand
         store = any(m in self._need_embeddings for m in self.metrics)
         if self.stem_reference_pca is None:
-            self.stem_projection.partial_fit(ref.embeddings)
+            self.stem_projection.partial_fit(ref)          # the container's own statistics: no second pass
             self.stem_reference_pca = self._project(self.stem_projection, ref.embeddings, store)
         return self.stem_reference_pca, self._project(self.stem_projection, cand.embeddings, store)
 
@@ -141,7 +141,7 @@ class AudioMetrics:
         if self.mix_projection is None:
             return ref, anti_ref, cand
         if self.mix_reference_pca is None:
-            self.mix_projection.partial_fit(ref.embeddings)
+            self.mix_projection.partial_fit(ref)
             self.mix_reference_pca = self._project(self.mix_projection, ref.embeddings, False)
             self.mix_anti_reference_pca = self._project(self.mix_projection, anti_ref.embeddings, False)
         return (self.mix_reference_pca, self.mix_anti_reference_pca,

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG.parent / "build" / "obj"
 LIB = PKG / "libamb200.so"
-SOURCES = ["common.cu", "pack.cu", "prdc.cu", "kd.cu", "cov.cu", "cov_tc.cu", "fad.cu", "host.cu"]
+SOURCES = ["common.cu", "pack.cu", "prdc.cu", "kd.cu", "cov.cu", "cov_tc.cu", "fad.cu", "pca.cu", "host.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

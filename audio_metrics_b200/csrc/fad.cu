@@ -17,6 +17,7 @@
 // pair per round of a round-robin tournament, a grid barrier separates rounds.
 #include <cooperative_groups.h>
 #include <cstdlib>
+#include <mutex>
 
 #include "internal.cuh"
 
@@ -472,8 +473,23 @@ __constant__ double kPolarCoef[kPolarSteps][3] = {
     {15.0 / 8, -10.0 / 8, 3.0 / 8},
 };
 
-constexpr int kPgM = 32, kPgN = 64, kPgK = 16, kPgThreads = 128;
+constexpr int kPgM = 32, kPgN = 64, kPgK = 16, kPgThreads = 256, kPgStages = 4;
 constexpr int kPolarPad = 64;   // iteration matrices are dp x dp, dp = d rounded up to 64, zero padded
+constexpr int kPgAStride = kPgM + 2;    // doubles per k row of the A tile, TN form ([k][i]); even: 16 B aligned rows
+constexpr int kPgA2Stride = kPgK + 2;   // doubles per i row of the A tile, NN form ([i][k])
+constexpr int kPgBStride = kPgN + 2;
+constexpr int kPgATile = (kPgK * kPgAStride > kPgM * kPgA2Stride ? kPgK * kPgAStride : kPgM * kPgA2Stride);
+constexpr int kPgStageDoubles = kPgATile + kPgK * kPgBStride;
+constexpr size_t kPgSmemBytes = size_t(kPgStages) * kPgStageDoubles * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // One CTA per matrix: alpha = |Mt|_F, X = Mt / alpha written into the zero-padded dp x dp buffer.
 __global__ void __launch_bounds__(1024)
@@ -482,6 +498,7 @@ polar_init_kernel(const double* __restrict__ Mt, int d, int dp, double* __restri
   __shared__ double s_inv;
   const long long mo = static_cast<long long>(blockIdx.x) * d * d;
   const long long xo = static_cast<long long>(blockIdx.x) * dp * dp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   double s = 0.0;
   for (long long e = threadIdx.x; e < static_cast<long long>(d) * d; e += blockDim.x) {
     const double v = Mt[mo + e];
@@ -489,116 +506,128 @@ polar_init_kernel(const double* __restrict__ Mt, int d, int dp, double* __restri
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  if (lane == 0) red[warp] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int w = 0; w < 32; ++w) t += red[w];
+    for (int w = 0; w < n_warps; ++w) t += red[w];
     s_inv = t > 0.0 ? 1.0 / sqrt(t) : 0.0;
   }
   __syncthreads();
   const double inv = s_inv;
-  for (long long e = threadIdx.x; e < static_cast<long long>(dp) * dp; e += blockDim.x) {
-    const int i = static_cast<int>(e / dp), j = static_cast<int>(e % dp);
-    X[xo + e] = (i < d && j < d) ? Mt[mo + static_cast<long long>(i) * d + j] * inv : 0.0;
+  for (int i = warp; i < dp; i += n_warps) {     // a warp per row: no integer divisions
+    double* x = X + xo + static_cast<long long>(i) * dp;
+    const double* m = Mt + mo + static_cast<long long>(i) * d;
+    for (int j = lane; j < dp; j += 32) x[j] = (i < d && j < d) ? m[j] * inv : 0.0;
   }
 }
 
 // fp64 GEMM tile kernel of the polar iteration on padded dp x dp row-major matrices (batch in z):
-//   MODE 0:  C = X^T X                       C[i][j] = sum_k X[k][i] X[k][j]
-//   MODE 1:  C = X (ca I + cb A + cc A2)     C[i][j] = sum_k X[i][k] Q[k][j], Q formed while loading
-// 32 x 64 output tile, 128 threads, 4 x 4 outputs per thread, k blocks of 16 double-buffered in
-// shared memory (global -> registers -> shared overlaps the FMAs of the current block).  At d = 512
-// that is 128 CTAs, one wave; the FP64 pipe (64 FMA/clk/SM) is the bound.
+//   MODE 0:  C = X^T X                            C[i][j] = sum_k X[k][i] X[k][j]
+//   MODE 1:  C = ca I + cb X + cc X^T X           (X = A symmetric: the quintic's matrix Q from A and A^2,
+//                                                  formed in the epilogue so that no GEMM loads need arithmetic)
+//   MODE 2:  C = X Q                              C[i][j] = sum_k X[i][k] Q[k][j]
+// 32 x 64 output tile per CTA, k blocks of 16 through a four-stage cp.async ring (every operand tile
+// is a plain copy of 16-byte pieces, so the L2 latency of a stage hides behind three stages of FMAs);
+// 256 threads = two groups of four warps that split each k block between them (even / odd k) and
+// add their 4 x 4 accumulators at the end: two warps per scheduler instead of one keep the FP64 pipe
+// fed across shared-memory and barrier latencies.  A thread's columns are {2 tx, 2 tx + 1, 32 + 2 tx,
+// 33 + 2 tx}: its two 16-byte reads of a B row are conflict free.  At d = 512: 128 CTAs, one wave.
 template <int MODE>
 __global__ void __launch_bounds__(kPgThreads)
-polar_gemm_kernel(const double* __restrict__ X, const double* __restrict__ A, const double* __restrict__ A2,
-                  double* __restrict__ C, int dp, int step) {
-  __shared__ __align__(16) double As[2][kPgK][kPgM + 2];
-  __shared__ __align__(16) double Bs[2][kPgK][kPgN + 2];
+polar_gemm_kernel(const double* __restrict__ X, const double* __restrict__ Q, double* __restrict__ C, int dp, int step) {
+  extern __shared__ __align__(16) double pg_smem[];
   const long long mo = static_cast<long long>(blockIdx.z) * dp * dp;
   X += mo;
   C += mo;
-  if (MODE == 1) { A += mo; A2 += mo; }
-  const double ca = MODE == 1 ? kPolarCoef[step][0] : 0.0;
-  const double cb = MODE == 1 ? kPolarCoef[step][1] : 0.0;
-  const double cc = MODE == 1 ? kPolarCoef[step][2] : 0.0;
+  if (MODE == 2) Q += mo;
   const int i0 = blockIdx.y * kPgM, j0 = blockIdx.x * kPgN;
-  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
-  const int l_row = t >> 3, l_c4 = (t & 7) * 4, l_c8 = (t & 7) * 8;   // direct loads: row of the k block, column offset
-  const int l_ii = t >> 2, l_k4 = (t & 3) * 4;                         // transposing load of X[i][k] (MODE 1)
+  const int tid = threadIdx.x, grp = tid >> 7, t = tid & 127, ty = t >> 4, tx = t & 15;
+  const double* Bsrc = MODE == 2 ? Q : X;
+  // this thread's 16-byte pieces of a stage: one of the A tile, two of the B tile
+  const int a_row = MODE == 2 ? (tid >> 3) : (tid >> 4);          // NN: 32 rows x 8 pieces; TN: 16 rows x 16 pieces
+  const int a_col = MODE == 2 ? (tid & 7) * 2 : (tid & 15) * 2;   // in doubles
+  const int b_row = tid >> 4, b_col = (tid & 15) * 4;             // 16 rows x 32 pieces, two adjacent per thread
+  auto issue = [&](int kb) {
+    double* st = pg_smem + static_cast<size_t>(kb % kPgStages) * kPgStageDoubles;
+    const int k0 = kb * kPgK;
+    if (MODE == 2) cp_async16(st + a_row * kPgA2Stride + a_col, X + static_cast<long long>(i0 + a_row) * dp + k0 + a_col);
+    else cp_async16(st + a_row * kPgAStride + a_col, X + static_cast<long long>(k0 + a_row) * dp + i0 + a_col);
+    double* bs = st + kPgATile + b_row * kPgBStride + b_col;
+    const double* bg = Bsrc + static_cast<long long>(k0 + b_row) * dp + j0 + b_col;
+    cp_async16(bs, bg);
+    cp_async16(bs + 2, bg + 2);
+  };
   double acc[4][4];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-  double ra[4], rb[8];
-  auto load = [&](int k0) {
-    if (MODE == 0) {
-      const double2* pa = reinterpret_cast<const double2*>(X + static_cast<long long>(k0 + l_row) * dp + i0 + l_c4);
-      const double2 a0 = pa[0], a1 = pa[1];
-      ra[0] = a0.x; ra[1] = a0.y; ra[2] = a1.x; ra[3] = a1.y;
-      const double2* pb = reinterpret_cast<const double2*>(X + static_cast<long long>(k0 + l_row) * dp + j0 + l_c8);
+  const int n_kb = dp / kPgK;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { const double2 b = pb[e]; rb[2 * e] = b.x; rb[2 * e + 1] = b.y; }
-    } else {
-      const double2* pa = reinterpret_cast<const double2*>(X + static_cast<long long>(i0 + l_ii) * dp + k0 + l_k4);
-      const double2 a0 = pa[0], a1 = pa[1];
-      ra[0] = a0.x; ra[1] = a0.y; ra[2] = a1.x; ra[3] = a1.y;
-      const long long o = static_cast<long long>(k0 + l_row) * dp + j0 + l_c8;
-      const double2* p1 = reinterpret_cast<const double2*>(A + o);
-      const double2* p2 = reinterpret_cast<const double2*>(A2 + o);
+  for (int s = 0; s < kPgStages - 1; ++s) {
+    if (s < n_kb) issue(s);
+    cp_async_commit();
+  }
+  for (int kb = 0; kb < n_kb; ++kb) {
+    cp_async_wait<kPgStages - 2>();     // this thread's pieces of stage kb have landed ...
+    __syncthreads();                    // ... everyone's have, and everyone is done with stage kb - 1
+    if (kb + kPgStages - 1 < n_kb) issue(kb + kPgStages - 1);   // refill the buffer stage kb - 1 used
+    cp_async_commit();
+    const double* st = pg_smem + static_cast<size_t>(kb % kPgStages) * kPgStageDoubles;
+    const double* bs = st + kPgATile;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const double2 u = p1[e], v = p2[e];
-        rb[2 * e] = fma(cc, v.x, cb * u.x);
-        rb[2 * e + 1] = fma(cc, v.y, cb * u.y);
+    for (int q = 0; q < kPgK / 2; ++q) {
+      const int kk = 2 * q + grp;
+      double a[4];
+      if (MODE == 2) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = st[(ty * 4 + r) * kPgA2Stride + kk];
+      } else {
+        const double2 a0 = *reinterpret_cast<const double2*>(st + kk * kPgAStride + ty * 4);
+        const double2 a1 = *reinterpret_cast<const double2*>(st + kk * kPgAStride + ty * 4 + 2);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y;
       }
-      const int dj = k0 + l_row - (j0 + l_c8);   // diagonal element of Q inside this thread's 8 columns?
-#pragma unroll
-      for (int e = 0; e < 8; ++e) rb[e] += (e == dj) ? ca : 0.0;
-    }
-  };
-  auto store = [&](int buf) {
-    if (MODE == 0) {
-      *reinterpret_cast<double2*>(&As[buf][l_row][l_c4]) = make_double2(ra[0], ra[1]);
-      *reinterpret_cast<double2*>(&As[buf][l_row][l_c4 + 2]) = make_double2(ra[2], ra[3]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) As[buf][l_k4 + e][l_ii] = ra[e];
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      *reinterpret_cast<double2*>(&Bs[buf][l_row][l_c8 + 2 * e]) = make_double2(rb[2 * e], rb[2 * e + 1]);
-  };
-  load(0);
-  store(0);
-  __syncthreads();
-  for (int k0 = 0; k0 < dp; k0 += kPgK) {
-    const int buf = (k0 / kPgK) & 1;
-    const bool more = k0 + kPgK < dp;
-    if (more) load(k0 + kPgK);
-#pragma unroll
-    for (int kk = 0; kk < kPgK; ++kk) {
-      const double2 a0 = *reinterpret_cast<const double2*>(&As[buf][kk][ty * 4]);
-      const double2 a1 = *reinterpret_cast<const double2*>(&As[buf][kk][ty * 4 + 2]);
-      const double2 b0 = *reinterpret_cast<const double2*>(&Bs[buf][kk][tx * 4]);
-      const double2 b1 = *reinterpret_cast<const double2*>(&Bs[buf][kk][tx * 4 + 2]);
-      const double a[4] = {a0.x, a0.y, a1.x, a1.y};
+      const double2 b0 = *reinterpret_cast<const double2*>(bs + kk * kPgBStride + 2 * tx);
+      const double2 b1 = *reinterpret_cast<const double2*>(bs + kk * kPgBStride + 32 + 2 * tx);
       const double b[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
     }
-    if (more) store(buf ^ 1);
-    __syncthreads();
   }
+  cp_async_wait<0>();
+  __syncthreads();
+  // add the two k groups (through the now idle ring) and write the tile
+  double* red = pg_smem;   // [128][16]
+  if (grp == 1) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    double* out = C + static_cast<long long>(i0 + ty * 4 + r) * dp + j0 + tx * 4;
-    *reinterpret_cast<double2*>(out) = make_double2(acc[r][0], acc[r][1]);
-    *reinterpret_cast<double2*>(out + 2) = make_double2(acc[r][2], acc[r][3]);
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) red[(r * 4 + c) * 128 + t] = acc[r][c];
+  }
+  __syncthreads();
+  if (grp == 0) {
+    const double ca = MODE == 1 ? kPolarCoef[step][0] : 0.0;
+    const double cb = MODE == 1 ? kPolarCoef[step][1] : 0.0;
+    const double cc = MODE == 1 ? kPolarCoef[step][2] : 1.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int gi = i0 + ty * 4 + r;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int gj = j0 + 32 * h + 2 * tx;
+        double v0 = acc[r][2 * h] + red[(r * 4 + 2 * h) * 128 + t];
+        double v1 = acc[r][2 * h + 1] + red[(r * 4 + 2 * h + 1) * 128 + t];
+        if (MODE == 1) {
+          const double2 x = *reinterpret_cast<const double2*>(X + static_cast<long long>(gi) * dp + gj);
+          v0 = fma(cc, v0, cb * x.x) + (gi == gj ? ca : 0.0);
+          v1 = fma(cc, v1, cb * x.y) + (gi == gj + 1 ? ca : 0.0);
+        }
+        *reinterpret_cast<double2*>(C + static_cast<long long>(gi) * dp + gj) = make_double2(v0, v1);
+      }
+    }
   }
 }
 
@@ -610,18 +639,29 @@ static int launch_polar(cudaStream_t st, const double* Mt, int d, int batch, dou
   double* X = bufs;
   double* Xn = bufs + mat;
   double* A = bufs + 2 * mat;
-  double* A2 = bufs + 3 * mat;
+  double* Qm = bufs + 3 * mat;
   int rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  auto set_attr = [] {
+    cudaError_t e = cudaFuncSetAttribute(polar_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPgSmemBytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(polar_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPgSmemBytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(polar_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPgSmemBytes));
+    return e;
+  };
+  std::call_once(once, [&] { attr_err = set_attr(); });
+  if (attr_err == cudaSuccess) attr_err = set_attr();   // the attribute is per device
+  if ((rc = check_cuda(attr_err, "cudaFuncSetAttribute(polar_gemm)"))) return rc;
   polar_init_kernel<<<batch, 1024, 0, st>>>(Mt, d, dp, X);
   if ((rc = check_launch("polar_init_kernel"))) return rc;
   const dim3 grid(dp / kPgN, dp / kPgM, batch);
   for (int k = 0; k < kPolarSteps; ++k) {
-    polar_gemm_kernel<0><<<grid, kPgThreads, 0, st>>>(X, nullptr, nullptr, A, dp, k);      // A  = X^T X
+    polar_gemm_kernel<0><<<grid, kPgThreads, kPgSmemBytes, st>>>(X, nullptr, A, dp, k);     // A = X^T X
     if ((rc = check_launch("polar_gemm_kernel<0>"))) return rc;
-    polar_gemm_kernel<0><<<grid, kPgThreads, 0, st>>>(A, nullptr, nullptr, A2, dp, k);     // A2 = A^T A = A^2
-    if ((rc = check_launch("polar_gemm_kernel<0>"))) return rc;
-    polar_gemm_kernel<1><<<grid, kPgThreads, 0, st>>>(X, A, A2, Xn, dp, k);                // X  = X q_k(A)
+    polar_gemm_kernel<1><<<grid, kPgThreads, kPgSmemBytes, st>>>(A, nullptr, Qm, dp, k);    // Q = a I + b A + c A^2
     if ((rc = check_launch("polar_gemm_kernel<1>"))) return rc;
+    polar_gemm_kernel<2><<<grid, kPgThreads, kPgSmemBytes, st>>>(X, Qm, Xn, dp, k);         // X <- X Q
+    if ((rc = check_launch("polar_gemm_kernel<2>"))) return rc;
     double* tmp = X; X = Xn; Xn = tmp;
   }
   *u_out = X;
@@ -629,31 +669,36 @@ static int launch_polar(cudaStream_t st, const double* Mt, int d, int batch, dou
 }
 
 // one block per pair: a = |mu_x-mu_y|^2, b = tr S_x + tr S_y, c = <U, M>_F  (U: dp-strided polar factor)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 fad_combine_polar_kernel(int d, int dp, const double* __restrict__ mu_x, const double* __restrict__ cov_x,
                          const double* __restrict__ mu_y, const double* __restrict__ cov_y,
                          const double* __restrict__ Mt, const double* __restrict__ U, double* __restrict__ out) {
-  __shared__ double red[256];
+  __shared__ double red[32];
   const int b = blockIdx.x;
   const long long mo = static_cast<long long>(b) * d * d;
   const long long uo = static_cast<long long>(b) * dp * dp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   double acc = 0.0;
   for (int k = threadIdx.x; k < d; k += blockDim.x) {
     const double df = mu_x[static_cast<long long>(b) * d + k] - mu_y[static_cast<long long>(b) * d + k];
     acc += df * df + cov_x[mo + static_cast<long long>(k) * d + k] + cov_y[mo + static_cast<long long>(k) * d + k];
   }
-  double c = 0.0;
-  for (long long e = threadIdx.x; e < static_cast<long long>(d) * d; e += blockDim.x) {
-    const int i = static_cast<int>(e / d), j = static_cast<int>(e % d);
-    c = fma(U[uo + static_cast<long long>(i) * dp + j], Mt[mo + e], c);
+  double c = 0.0;   // a warp per row: coalesced, no integer divisions, fixed order
+  for (int i = warp; i < d; i += n_warps) {
+    const double* u = U + uo + static_cast<long long>(i) * dp;
+    const double* m = Mt + mo + static_cast<long long>(i) * d;
+    for (int j = lane; j < d; j += 32) c = fma(u[j], m[j], c);
   }
-  red[threadIdx.x] = acc - 2.0 * c;
+  acc -= 2.0 * c;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) red[warp] = acc;
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < n_warps; ++w) t += red[w];
+    out[b] = t;
   }
-  if (threadIdx.x == 0) out[b] = red[0];
 }
 
 // one block per pair: a = |mu_x-mu_y|^2, b = tr S_x + tr S_y, c = sum_j |m_j|
@@ -721,7 +766,7 @@ static int launch_jacobi_block(cudaStream_t st, int dev, double* Gt, int d, int 
 // — so cosines below 1e-8 leave it exact to fp64 round-off, and the sweep that only confirms
 // convergence can be dropped.  Eigen-FACTORS (the AMB_FAD_FACTOR=eig path) are first order in the
 // cosines and keep the 1e-14 test and the confirming sweep.
-static int launch_jacobi(cudaStream_t st, int dev, double* Gt, int d, int n_mat, int* counters, bool values_only) {
+int launch_jacobi(cudaStream_t st, int dev, double* Gt, int d, int n_mat, int* counters, bool values_only) {
   double tol = values_only ? 1e-8 : 1e-14;
   int stop_rot = values_only ? d / 8 : 0;
   int* rot = counters;
@@ -852,7 +897,7 @@ int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu
   } else {                            // polar iteration: c = <U, M>
     const double* U = nullptr;
     if ((rc = launch_polar(st, Mt, d, batch, polar_bufs, &U))) return rc;
-    fad_combine_polar_kernel<<<batch, 256, 0, st>>>(d, static_cast<int>(round_up_ll(d, kPolarPad)), mu_x, cov_x, mu_y,
+    fad_combine_polar_kernel<<<batch, 1024, 0, st>>>(d, static_cast<int>(round_up_ll(d, kPolarPad)), mu_x, cov_x, mu_y,
                                                      cov_y, Mt, U, out);
     if ((rc = check_launch("fad_combine_polar_kernel"))) return rc;
   }

@@ -84,6 +84,12 @@ int launch_pack(cudaStream_t stream, const void* src, int dtype, long long ld, i
                 long long n_rows_out, __half* planes, long long plane_halfs, int kb_count,
                 float* inv_scale, float* norm, float* rho, int* row_exp, float* cmin);
 
+// One-sided (Hestenes) Jacobi on the columns of n_mat d x d fp64 matrices stored as rows of Gt
+// (fad.cu).  counters: kJacobiCounters zeroed-by-callee ints.  values_only: loose stopping rule that
+// is exact for the SUM of the column norms; otherwise columns are orthogonalised to 1e-14.
+constexpr int kJacobiCounters = 64;
+int launch_jacobi(cudaStream_t st, int dev, double* Gt, int d, int n_mat, int* counters, bool values_only);
+
 // Integer tensor-core Gram / column sums of an fp32 matrix (cov_tc.cu).
 size_t cov_tc_ws_bytes(long long n, int d);
 int cov_tc_accumulate(cudaStream_t st, int dev, const float* X, long long n, int d, long long ld, double* sum,

@@ -203,28 +203,48 @@ class _Shard:
         return self.ops.container(gathered)
 
 
+def _width(c):
+    """Embedding width of a container, None if it has never seen a row."""
+    if c._buf is not None:
+        return c._buf.shape[1]
+    if c.n and c.mean is not None:
+        return c.mean.shape[0]
+    return None
+
+
 class _Held:
     """A row shard held by an AudioMetricsData (evaluate_containers): statistics come from the
     container, derived data is cached on it and dropped when rows are added."""
 
-    def __init__(self, c, n_total, ops):
+    def __init__(self, c, n_total, ops, d=None):
         self.c, self.n_total, self.ops = c, n_total, ops
         self.cache = c._cache
-        mean = c.mean if c._buf is None else None
-        self.d = c._buf.shape[1] if c._buf is not None else mean.shape[0]
+        self.empty = not c.n                       # this rank holds no rows of the set (tiny sets, many ranks)
+        self.d = _width(c) or d
         self.device = c.device
 
     def rows(self):
+        if self.empty:
+            return torch.empty((0, self.d), dtype=torch.float32, device=self.device)
         x = self.c.embeddings
         if x is None:
             raise ValueError("this metric needs stored embeddings (store_embeddings=True)")
         return x
 
     def moments(self):
+        if self.empty:
+            return torch.zeros(self.d + self.d * self.d, dtype=torch.float64, device=self.device)
         return self.c.local_moments()
 
     def full_container(self, gathered):
-        return self.c if gathered is None else self.ops.container(gathered)
+        return self.ops.container(gathered)
+
+    def stats(self):
+        """(mean, cov) of the rows held here — final on one GPU, no moment exchange needed."""
+        mean, cov = self.c.mean, self.c.cov
+        if tuple(cov.shape) != (self.d, self.d):
+            cov = torch.zeros((self.d, self.d), dtype=torch.float64, device=mean.device)
+        return mean, cov
 
 
 def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=100, kd_subset_size=1000,
@@ -242,14 +262,15 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
 
     def full(s, n):
         """(container over ALL rows of the set, this rank's row range) — gathered once per set."""
+        if world == 1 and isinstance(s, _Held):
+            return s.c, 0, n, n              # the container itself (never cached inside itself: no cycles)
         key = ("full", world, id(group))
         hit = s.cache.get(key)
         if hit is None:
             row0, nrows, chunk = shard_rows(n, world, rank)
             rows = s.rows()
             assert rows.shape[0] == nrows, "shards must follow shard_rows()"
-            gathered = None if world == 1 and isinstance(s, _Held) else _allgather_rows(rows, n, chunk, group)
-            hit = s.cache[key] = (s.full_container(gathered), row0, nrows, chunk)
+            hit = s.cache[key] = (s.full_container(_allgather_rows(rows, n, chunk, group)), row0, nrows, chunk)
         return hit
 
     def radii(s, n):
@@ -272,26 +293,30 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
             if all(s is not t for t in stat_sets):
                 stat_sets.append(s)
     stat_sets.sort(key=lambda s: s is cand)                     # the candidate's moments last
+    local_stats = world == 1 and all(isinstance(s, _Held) for s in stat_sets)   # statistics are already final
     moms = []
     done_ref_sweep = False
     for s in stat_sets:
         if s is cand and want_prdc and not done_ref_sweep:
             r_ref = radii(ref, n_ref)
             done_ref_sweep = True
-        moms.append(s.moments())
+        moms.append(s.stats() if local_stats else s.moments())
     if want_prdc and not done_ref_sweep:
         r_ref = radii(ref, n_ref)
     if fad_pairs:
-        sizes = [s.d + s.d * s.d for s in stat_sets]
-        mom = torch.cat(moms) if len(moms) > 1 else moms[0]
-        _allreduce(mom, group)                                  # one message: sum of (d + d^2) doubles per set
-        stats, off = [], 0
-        for s, sz in zip(stat_sets, sizes):
-            stats.append(ops.stats_from_moments(mom[off:off + sz], s.n_total, s.d))
-            off += sz
+        if local_stats:
+            stats = moms
+        else:
+            sizes = [s.d + s.d * s.d for s in stat_sets]
+            mom = torch.cat(moms) if len(moms) > 1 else moms[0]
+            _allreduce(mom, group)                              # one message: sum of (d + d^2) doubles per set
+            stats, off = [], 0
+            for s, sz in zip(stat_sets, sizes):
+                stats.append(ops.stats_from_moments(mom[off:off + sz], s.n_total, s.d))
+                off += sz
+            pending["_mom"] = mom
         lookup = lambda s: stats[[t is s for t in stat_sets].index(True)]
         pending["fad"] = ops.frechet_batch([(lookup(x), lookup(y)) for _, x, y in fad_pairs])
-        pending["_mom"] = mom
 
     # ---- PRDC
     def counts(list_cap):
@@ -392,18 +417,29 @@ def evaluate_containers(ref, cand, metrics=("fad", "kd", "prdc"), nearest_k=5, g
     ops = default_ops(some.device)
     world, _ = _world(group)
 
-    def total(c):
+    def sizes(c):
+        """(rows over all ranks, embedding width) — two tiny collectives, once per container state."""
         if world == 1:
-            return c.n
-        t = torch.tensor([c.n or 0], dtype=torch.int64, device=ops.device)
-        _allreduce(t, group)
-        return int(t)
+            return c.n, _width(c)
+        t = torch.tensor([c.n or 0, _width(c) or 0], dtype=torch.int64, device=ops.device)
+        n = t[:1].clone()
+        _allreduce(n, group)
+        _allreduce(t, group, dist.ReduceOp.MAX)
+        return int(n), int(t[1])
+
+    views = {}
 
     def held(c):
-        hit = c._cache.get(("held", world, id(group)))
-        if hit is None or hit.n_total is None:
-            hit = c._cache[("held", world, id(group))] = _Held(c, total(c), ops)
-        return hit
+        # (a view per call: caching it on the container would tie the container into a reference
+        #  cycle, and its device buffers would then wait for the cyclic garbage collector)
+        v = views.get(id(c))
+        if v is None:
+            key = ("sizes", world, id(group))
+            if key not in c._cache:
+                c._cache[key] = sizes(c)
+            n_total, d = c._cache[key]
+            v = views[id(c)] = _Held(c, n_total, ops, d)
+        return v
 
     extra = []
     if apa is not None:

@@ -323,6 +323,16 @@ def run_b200_arm(args):
     ref_host = ref_shard.cpu().pin_memory()
     cand_host = cand_shard.cpu().pin_memory()
     step(ref_host, cand_host)
+    if os.environ.get("AMB_BENCH_TRACE"):
+        for i in range(4):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); step(ref_host, cand_host); torch.cuda.synchronize()
+            sys.stderr.write(f"[trace] e2e step {i}: {(time.perf_counter() - t0) * 1e3:.2f} ms\n")
+        for i in range(3):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); step(ref_shard, cand_shard); torch.cuda.synchronize()
+            sys.stderr.write(f"[trace] device step {i}: {(time.perf_counter() - t0) * 1e3:.2f} ms\n")
+        for m in ("fad", "kd"):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); step(ref_shard, cand_shard, metrics=(m,)); torch.cuda.synchronize()
+            sys.stderr.write(f"[trace] device {m} step: {(time.perf_counter() - t0) * 1e3:.2f} ms\n")
     ms_e2e, result_e2e = timed(lambda: step(ref_host, cand_host), max(1, min(args.steps, 3)))
     h2d = (ref_host.numel() + cand_host.numel()) * 4
     d2h = 8 * 8 + 8 * KD_SUBSETS   # result scalars + the 100 per-subset MMDs

@@ -111,6 +111,21 @@ int amb_frechet(int dev, amb_stream_t stream, int batch, int d, const double* mu
                 const double* cov_x, const double* mu_y, const double* cov_y, double* out, void* ws,
                 size_t ws_bytes);
 
+/* ------------------------------------------------------------------ PCA projection
+ * IncrementalPCA.partial_fit / transform (projection.py:6-46, used at audio_metrics.py:163-209).
+ * The principal axes are the eigenvectors of the d x d scatter matrix (amb_cov_* give it), so
+ * the fit is one symmetric eigen-decomposition and the projection one pass over the rows.
+ *
+ * amb_sym_eig: eigen-decomposition of a symmetric positive semi-definite S [d, d] (fp64) by
+ * one-sided Jacobi.  evals[d] descending; evecs[d, d]: row i = unit eigenvector of evals[i], with
+ * sklearn's svd_flip(u_based_decision=False) sign (largest-magnitude entry of the row positive).
+ * amb_pca_transform: out[n, k] (fp64) = (X - mean) components^T, components [k, d] fp64. */
+size_t amb_sym_eig_ws_bytes(int d);
+int amb_sym_eig(int dev, amb_stream_t stream, int d, const double* S, double* evals, double* evecs,
+                void* ws, size_t ws_bytes);
+int amb_pca_transform(int dev, amb_stream_t stream, const void* X, int dtype, long long n, int d,
+                      long long ld, const double* mean, const double* components, int k, double* out);
+
 /* --------------------------------------------------------------- packed operands
  * Embeddings are rewritten once per set into the tensor-core operand format
  * (two fp16 planes with one power-of-two scale per 256-row tile, plus per-row

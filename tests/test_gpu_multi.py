@@ -1,0 +1,71 @@
+"""Hardware test of the row-sharded path: two ranks over NCCL against the single-GPU result
+(skipped on a box with fewer than two GPUs).  The gloo test (test_dist_cpu.py) covers the same
+reduction logic with stand-in kernels; this one runs the product kernels and NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_ref, n_cand, d, k, out):
+    import torch.distributed as dist
+
+    from audio_metrics_b200 import AudioMetricsData
+    from audio_metrics_b200.dist import evaluate_containers, evaluate_sharded, shard_rows
+    from audio_metrics_b200.synth import make_sets_numpy
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        ref, cand = make_sets_numpy(n_ref, n_cand, d, seed=77)
+        r0, rn, _ = shard_rows(n_ref, world, rank)
+        c0, cn, _ = shard_rows(n_cand, world, rank)
+        R, C = AudioMetricsData(True, dev), AudioMetricsData(True, dev)
+        R.add(torch.from_numpy(ref[r0:r0 + rn]))
+        C.add(torch.from_numpy(cand[c0:c0 + cn]))        # (700, 130): rank 1 holds no candidate rows at all
+        a = evaluate_containers(R, C, ("fad", "kd", "prdc"), nearest_k=k, kd_subsets=12, kd_subset_size=200)
+        b = evaluate_sharded(torch.from_numpy(ref[r0:r0 + rn]).to(dev), torch.from_numpy(cand[c0:c0 + cn]).to(dev),
+                             n_ref, n_cand, nearest_k=k, kd_subsets=12, kd_subset_size=200)
+        out[rank] = (a, b)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_ref,n_cand", [(3000, 2500), (700, 130)])
+def test_two_ranks_equal_one(cuda_device, n_ref, n_cand):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    from audio_metrics_b200 import AudioMetricsData
+    from audio_metrics_b200.dist import evaluate_containers
+    from audio_metrics_b200.synth import make_sets_numpy
+
+    d, k, world = 128, 5, 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n_ref, n_cand, d, k, out), nprocs=world, join=True)
+    ref, cand = make_sets_numpy(n_ref, n_cand, d, seed=77)
+    R, C = AudioMetricsData(True), AudioMetricsData(True)
+    R.add(torch.from_numpy(ref)); C.add(torch.from_numpy(cand))
+    want = evaluate_containers(R, C, ("fad", "kd", "prdc"), nearest_k=k, kd_subsets=12, kd_subset_size=200)
+    for rank in range(world):
+        for got in out[rank]:
+            assert got["fad"] == pytest.approx(want["fad"], rel=1e-9)
+            for key in ("kernel_distance_mean", "kernel_distance_std"):
+                assert got[key] == pytest.approx(want[key], rel=1e-9), key
+            for key in ("precision", "recall", "density", "coverage"):
+                assert got[key] == want[key], key      # ratios of exact integer counts: identical
