@@ -31,6 +31,7 @@ SIGNATURES = {
     "amb_profile_read": (_i, [_vp]),
     "amb_cov_ws_bytes": (_sz, [_ll, _i]),
     "amb_cov_accumulate": (_i, [_i, _vp, _vp, _i, _ll, _i, _ll, _vp, _vp, _vp, _sz]),
+    "amb_cov_accumulate_masked": (_i, [_i, _vp, _vp, _i, _ll, _i, _ll, _vp, _i, _vp, _vp]),
     "amb_cov_finalize": (_i, [_i, _vp, _ll, _i, _vp, _vp, _vp, _vp]),
     "amb_stats_merge": (_i, [_i, _vp, _i, _ll, _vp, _vp, _ll, _vp, _vp, _vp]),
     "amb_frechet_ws_bytes": (_sz, [_i, _i]),

@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from .data import AudioMetricsData
 from .embedders import DEFAULT_EMBEDDER, EMBEDDERS
-from .dist import evaluate_containers
+from .dist import evaluate_containers, evaluate_devices
 from .metrics.apa import _apa
 from .mix import DEFAULT_MIX_FUNCTION, MIX_FUNCTIONS
 from .pipeline import ItemCategory, embedding_pipeline
@@ -26,6 +26,9 @@ class AudioMetrics:
     def __init__(self, metrics=["apa", "fad"], n_pca=None, device_indices=None, embedder=None, mix_function=None,
                  win_dur=5.0, input_sr=None):
         self.device = self._resolve_device(device_indices)
+        # device_indices with several entries (the reference's thread-per-GPU handler,
+        # util/gpu_parallel.py:20-76): the all-pairs sweeps of evaluate() are sharded over them
+        self.devices = [torch.device("cuda", int(i)) for i in device_indices] if device_indices else [self.device]
         self.metrics = metrics
         self.need_apa = "apa" in self.metrics
         self.win_dur = win_dur
@@ -65,7 +68,7 @@ class AudioMetrics:
     def save_state(self, fp: str | Path):
         """audio_metrics.py:78-91 — plain tensors / scalars so weights_only loading works."""
         state = dict(self.__dict__)
-        for k in ("mix_function", "embedder", "device"):
+        for k in ("mix_function", "embedder", "device", "devices"):
             state.pop(k, None)
         for attr in self._amd:
             if state.get(attr):
@@ -170,8 +173,12 @@ class AudioMetrics:
         # reference's one call and one host synchronisation per metric (:254-272); under
         # torch.distributed the containers hold this rank's rows and the step is row-sharded.
         fused = tuple(m for m in ("fad", "kd", "prdc") if m in self.metrics) if self.stems_mode else ()
-        res = evaluate_containers(stem_ref if fused else None, stem_cand if fused else None, fused,
-                                  nearest_k=None, apa=apa_sets)   # k = max(1, min(10, n_ref, n_cand)), :263
+        if len(self.devices) > 1 and not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            res = evaluate_devices(stem_ref if fused else None, stem_cand if fused else None, self.devices, fused,
+                                   nearest_k=None, apa=apa_sets)
+        else:
+            res = evaluate_containers(stem_ref if fused else None, stem_cand if fused else None, fused,
+                                      nearest_k=None, apa=apa_sets)   # k = max(1, min(10, n_ref, n_cand)), :263
         result = {}
         for key in ("fad", "kernel_distance_mean", "kernel_distance_std", "precision", "recall", "density",
                     "coverage"):

@@ -75,6 +75,77 @@ gram_tile_kernel(const T* __restrict__ X, long long n, int d, long long ld, int 
   }
 }
 
+// Small batches (the <= 32-row batches of the embedding pipeline, embed.py:226-236, up to a few
+// thousand rows): ONE launch that adds the batch's raw moments straight into the running
+// accumulators — sum[d] += column sums, gram[d][d] += X^T X (both triangles) — optionally of only
+// the rows whose category matches (mask[row] == mask_value: the pipeline's per-category boolean
+// mask, applied while loading instead of by an index_select beforehand).  One CTA per 128 x 128 tile
+// on or above the diagonal; every output element has exactly one writer, so the accumulation is
+// deterministic without atomics.  The reference finalises and Chan-merges a d x d covariance per
+// batch (data.py:37-47,77-94); here nothing is finalised until the statistics are read.
+template <typename T>
+__global__ void __launch_bounds__(256)
+moments_small_kernel(const T* __restrict__ X, long long n, int d, long long ld, const int32_t* __restrict__ mask,
+                     int mask_value, int nt, double* __restrict__ sum, double* __restrict__ gram) {
+  __shared__ __align__(16) double As[kGK][kGT];
+  __shared__ __align__(16) double Bs[kGK][kGT];
+  int tp = blockIdx.x, ti = 0;
+  while (tp >= nt - ti) { tp -= nt - ti; ++ti; }
+  const int tj = ti + tp;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  double acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+  double csum = 0.0;   // threads 0..127 of a diagonal tile: column sum of column ti*128 + tid
+  for (long long r = 0; r < n; r += kGK) {
+    for (int e = tid; e < kGK * kGT; e += 256) {
+      const int rr = e / kGT, cc = e % kGT;
+      const long long row = r + rr;
+      const bool live = row < n && (mask == nullptr || mask[row] == mask_value);
+      const int ca = ti * kGT + cc, cb = tj * kGT + cc;
+      As[rr][cc] = (live && ca < d) ? static_cast<double>(X[row * ld + ca]) : 0.0;
+      Bs[rr][cc] = (live && cb < d) ? static_cast<double>(X[row * ld + cb]) : 0.0;
+    }
+    __syncthreads();
+    if (ti == tj && tid < kGT) {
+#pragma unroll
+      for (int kk = 0; kk < kGK; ++kk) csum += As[kk][tid];
+    }
+#pragma unroll
+    for (int kk = 0; kk < kGK; ++kk) {
+      double a[8], b[8];
+#pragma unroll
+      for (int v = 0; v < 8; v += 2) {
+        const double2 av = *reinterpret_cast<const double2*>(&As[kk][ty * 8 + v]);
+        const double2 bv = *reinterpret_cast<const double2*>(&Bs[kk][tx * 8 + v]);
+        a[v] = av.x; a[v + 1] = av.y;
+        b[v] = bv.x; b[v + 1] = bv.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gi = ti * kGT + ty * 8 + i;
+    if (gi >= d) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gj = tj * kGT + tx * 8 + j;
+      if (gj >= d) continue;
+      gram[static_cast<long long>(gi) * d + gj] += acc[i][j];
+      if (ti != tj) gram[static_cast<long long>(gj) * d + gi] += acc[i][j];   // mirror of an off-diagonal tile
+    }
+  }
+  if (ti == tj && tid < kGT && ti * kGT + tid < d) sum[ti * kGT + tid] += csum;
+}
+
 // gram[i][j] += sum over slabs of the upper-tile partials, mirrored to the lower
 // triangle (tile granularity: inside a diagonal tile both halves were computed).
 __global__ void gram_reduce_kernel(const double* __restrict__ partial, int n_slabs, int d,
@@ -218,6 +289,23 @@ int amb_cov_accumulate(int dev, amb_stream_t stream, const void* X, int dtype, l
   if ((rc = check_launch("gram_reduce_kernel"))) return rc;
   colsum_reduce_kernel<<<(d + 255) / 256, 256, 0, st>>>(spart, slabs, d, sum);
   return check_launch("colsum_reduce_kernel");
+}
+
+int amb_cov_accumulate_masked(int dev, amb_stream_t stream, const void* X, int dtype, long long n, int d,
+                              long long ld, const int32_t* mask, int mask_value, double* sum, double* gram) {
+  if (!X || !sum || !gram || n <= 0 || d <= 0 || ld < d)
+    return set_error(AMB_ERR_ARG, "amb_cov_accumulate_masked: bad argument (n=%lld d=%d ld=%lld)", n, d, ld);
+  if (dtype != AMB_F32 && dtype != AMB_F64) return set_error(AMB_ERR_ARG, "amb_cov_accumulate_masked: bad dtype");
+  DeviceGuard guard(dev);
+  if (!guard.ok) return AMB_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nt = (d + kGT - 1) / kGT;
+  const unsigned grid = static_cast<unsigned>(nt * (nt + 1) / 2);
+  if (dtype == AMB_F32)
+    moments_small_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(X), n, d, ld, mask, mask_value, nt, sum, gram);
+  else
+    moments_small_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(X), n, d, ld, mask, mask_value, nt, sum, gram);
+  return check_launch("moments_small_kernel");
 }
 
 int amb_cov_finalize(int dev, amb_stream_t stream, long long n, int d, const double* sum,

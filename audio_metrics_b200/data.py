@@ -212,13 +212,21 @@ class AudioMetricsData:
         return xd, (ev, main)
 
     # ------------------------------------------------------------- statistics
-    def _moments(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
-        """out[d + d*d] (+)= raw fp64 moments (column sums | Gram) of a device batch."""
+    SMALL_BATCH = 2048     # rows up to which the one-launch moment kernel is used
+
+    def _moments(self, x: torch.Tensor, out: torch.Tensor = None, mask=None, mask_value=0) -> torch.Tensor:
+        """out[d + d*d] (+)= raw fp64 moments (column sums | Gram) of a device batch (of its rows
+        with mask == mask_value when an int32 device mask is given)."""
         dev = self.device
         n, d = x.shape
         L = _lib.lib()
         if out is None:
             out = torch.zeros(d + d * d, dtype=torch.float64, device=dev)
+        if mask is not None or n <= self.SMALL_BATCH:
+            _lib.check(L.amb_cov_accumulate_masked(dev.index, _lib.stream_ptr(dev), x.data_ptr(), _lib.dtype_code(x),
+                                                   n, d, x.stride(0), None if mask is None else mask.data_ptr(),
+                                                   int(mask_value), out.data_ptr(), out[d:].data_ptr()))
+            return out
         ws = _lib.workspace(L.amb_cov_ws_bytes(n, d), dev)
         _lib.check(L.amb_cov_accumulate(dev.index, _lib.stream_ptr(dev), x.data_ptr(), _lib.dtype_code(x), n, d,
                                         x.stride(0), out.data_ptr(), out[d:].data_ptr(), ws.data_ptr(), ws.numel()))
@@ -276,6 +284,25 @@ class AudioMetricsData:
             self._acc_n += n
             self._cache = {}
         self._n = (self._n or 0) + n
+
+    def add_masked(self, embeddings, mask, mask_value, count):
+        """``add(embeddings[mask == mask_value])`` for a device batch and an int32 device mask of which
+        ``count`` rows match (the caller built the mask on the host and knows the count): what the
+        embedding pipeline does per item category (embed.py:231-236), without materialising the
+        selection when only statistics are kept."""
+        if count == 0:
+            return
+        if self.store_embeddings:
+            sel = torch.nonzero(mask == int(mask_value)).squeeze(1)
+            return self.add(embeddings.index_select(0, sel))
+        x = _lib.as_device_matrix(embeddings, self.device)
+        d = x.shape[1]
+        if self._acc is not None and self._acc.numel() != d + d * d:
+            raise ValueError("embedding width changed between batches")
+        self._acc = self._moments(x, self._acc, mask=mask, mask_value=mask_value)
+        self._acc_n += int(count)
+        self._cache = {}
+        self._n = (self._n or 0) + int(count)
 
     def recompute_stats(self):
         """data.py:49-58 (n == 1 yields a (1, 1) zero covariance there; kept)."""

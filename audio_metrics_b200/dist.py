@@ -452,3 +452,102 @@ def evaluate_containers(ref, cand, metrics=("fad", "kd", "prdc"), nearest_k=5, g
     return _fused(ops, held(ref) if ref is not None else None, held(cand) if cand is not None else None, metrics,
                   nearest_k, group, extra_fad=extra, kd_subsets=kd_subsets, kd_subset_size=kd_subset_size,
                   kd_seed=kd_seed)
+
+
+# ------------------------------------------------------------------ one process, several GPUs
+def _replica(c, dev):
+    """A container with the same rows on another device of this process (peer copy over NVLink),
+    cached on the original so that a reference set is replicated — and swept — once."""
+    from .data import AudioMetricsData
+
+    if dev == c.device:
+        return c
+    key = ("replica", dev.index)
+    r = c._cache.get(key)
+    if r is None:
+        r = AudioMetricsData(store_embeddings=True, device=dev)
+        x = c.embeddings
+        with torch.cuda.device(dev):
+            r.embeddings = x.to(dev, non_blocking=True)
+        c._cache[key] = r
+    return r
+
+
+def evaluate_devices(ref, cand, devices, metrics=("fad", "kd", "prdc"), nearest_k=None, apa=None,
+                     kd_subsets=100, kd_subset_size=1000, kd_seed=1234):
+    """The fused step of ONE process over several GPUs — ``AudioMetrics(device_indices=[0, 1, ...])``.
+
+    The reference's only multi-GPU mechanism is thread-per-GPU data parallelism inside one process
+    (util/gpu_parallel.py:20-76), so the drop-in keeps that shape: no process group, one host thread
+    that enqueues asynchronous work on every device.  The containers live on ``devices[0]`` (where the
+    embedder produced them); their rows are replicated to the other devices by peer copies, every
+    device takes a 256-aligned row shard of both all-pairs sweeps against all columns, radii slices
+    and per-candidate counts travel back as small peer copies, and the N-independent parts (Frechet
+    distances, kernel distance) run on ``devices[0]`` beside them.  Same results as one device
+    (the counts are exact integers, the radii exact roundings)."""
+    from .metrics.kd import KID_COEF0, KID_DEGREE
+
+    devices = [torch.device(d) if not isinstance(d, torch.device) else d for d in devices]
+    world = len(devices)
+    dev0 = devices[0]
+    ops0 = default_ops(dev0)
+    want_prdc = "prdc" in metrics and ref is not None
+    rest = tuple(m for m in metrics if m != "prdc")
+    if world == 1 or not want_prdc:
+        return evaluate_containers(ref, cand, metrics, nearest_k=nearest_k, apa=apa, kd_subsets=kd_subsets,
+                                   kd_subset_size=kd_subset_size, kd_seed=kd_seed)
+    n_ref, n_cand = ref.n, cand.n
+    k = nearest_k if nearest_k is not None else max(1, min(10, n_ref, n_cand))
+    main0 = torch.cuda.current_stream(dev0)
+
+    # ---- replicate (reference first), then every device sweeps its row shard
+    def sweep_radii(c, n):
+        key = f"radii_{k}"
+        if c.radii.get(key) is not None:
+            return [_replica(c, d).radii.setdefault(key, c.radii[key].to(d, non_blocking=True)) for d in devices]
+        parts = []
+        for i, d in enumerate(devices):
+            row0, nrows, _ = shard_rows(n, world, i)
+            with torch.cuda.device(d):
+                parts.append(default_ops(d).radii_rows(_replica(c, d), row0, nrows, k))
+        full0 = torch.cat([p.to(dev0, non_blocking=True) for p in parts])      # peer copies of [n / world] floats
+        out = []
+        for d in devices:
+            with torch.cuda.device(d):
+                r = full0 if d == dev0 else full0.to(d, non_blocking=True)
+            _replica(c, d).radii[key] = r
+            out.append(r)
+        return out
+
+    r_ref = sweep_radii(ref, n_ref)
+    r_cand = sweep_radii(cand, n_cand)
+
+    def counts(list_cap):
+        cols, ts, uncs = [], [], []
+        for i, d in enumerate(devices):
+            row0, nrows, _ = shard_rows(n_ref, world, i)
+            with torch.cuda.device(d):
+                col, t, unc = default_ops(d).count_rows(_replica(ref, d), _replica(cand, d), r_ref[i], r_cand[i], row0,
+                                                        nrows, k, list_cap=list_cap)
+            cols.append(col); ts.append(t); uncs.append(unc)
+        with torch.cuda.device(dev0):
+            col = torch.stack([c.to(dev0, non_blocking=True) for c in cols]).sum(dim=0, dtype=torch.int64)
+            t = torch.stack([x.to(dev0, non_blocking=True) for x in ts]).sum(dim=0)
+            unc = torch.stack([x.to(dev0, non_blocking=True) for x in uncs]).max(dim=0).values   # lists are per device
+            return torch.cat([torch.stack([(col > 0).sum(), col.sum()]), t.to(torch.int64), unc.to(torch.int64)])
+
+    pending = counts(None)
+    # ---- the N-independent metrics on devices[0], queued behind its share of the sweeps
+    with torch.cuda.device(dev0):
+        result = evaluate_containers(ref if rest else None, cand if rest else None, rest, nearest_k=k, apa=apa,
+                                     kd_subsets=kd_subsets, kd_subset_size=kd_subset_size, kd_seed=kd_seed) \
+            if (rest or apa is not None) else {}
+        hits, total, recalled, covered, uncertain, cap = pending.tolist()
+        list_cap = None
+        while list_cap != EXACT and uncertain > cap:
+            list_cap = ops0.next_list_cap(uncertain, n_ref, n_cand)
+            hits, total, recalled, covered, uncertain, cap = counts(list_cap).tolist()
+    result.update(precision=hits / n_cand, recall=recalled / n_ref, density=(1.0 / float(k)) * (total / n_cand),
+                  coverage=covered / n_ref)                                        # prdc.py:36-48
+    del main0
+    return result

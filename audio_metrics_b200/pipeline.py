@@ -141,9 +141,20 @@ def embedding_pipeline(waveforms, embedder, mix_function, gpu_handler=None, apa_
     for batch in batch_accumulator(items, batch_size):
         emb = embedder.forward({"audio": batch["audio"]})["embedding"]
         cat = batch["category"]
+        cat_dev = None
         for c, dst in data.items():
             mask = cat == int(c)
-            if mask.any():   # embed.py:231-236, on the device the container lives on
+            count = int(mask.sum())
+            if not count:
+                continue
+            # embed.py:231-236, on the device the container lives on
+            if count == len(cat):
+                dst.add(emb)
+            elif dst.store_embeddings or not emb.is_cuda:
                 sel = torch.as_tensor(np.nonzero(mask)[0], device=emb.device)
                 dst.add(emb.index_select(0, sel))
+            else:   # statistics only: one masked moment launch per category, no selection copy
+                if cat_dev is None:
+                    cat_dev = torch.as_tensor(cat.astype(np.int32), device=emb.device)
+                dst.add_masked(emb, cat_dev, int(c), count)
     return data

@@ -89,6 +89,14 @@ int amb_get_option(const char* name);
 size_t amb_cov_ws_bytes(long long n, int d);
 int amb_cov_accumulate(int dev, amb_stream_t stream, const void* X, int dtype, long long n, int d,
                        long long ld, double* sum, double* gram, void* ws, size_t ws_bytes);
+/* The streaming form for the embedding pipeline's small batches (embed.py:226-236: <= 32 rows per
+ * call, one boolean mask per item category): ONE kernel launch, no workspace, that adds the raw
+ * moments of the rows with mask[row] == mask_value (mask == NULL: all rows) into sum / gram.
+ * Deterministic (one writer per element).  Meant for n up to a few thousand rows; larger batches
+ * are faster through amb_cov_accumulate. */
+int amb_cov_accumulate_masked(int dev, amb_stream_t stream, const void* X, int dtype, long long n, int d,
+                              long long ld, const int32_t* mask, int mask_value, double* sum,
+                              double* gram);
 /* mean = sum/n;  cov = (gram - n mean mean^T)/(n-1), zeros when n == 1
  * (data.py:39-44: torch.mean, torch.cov(correction=1), zeros for n == 1). */
 int amb_cov_finalize(int dev, amb_stream_t stream, long long n, int d, const double* sum,

@@ -69,3 +69,39 @@ def test_two_ranks_equal_one(cuda_device, n_ref, n_cand):
                 assert got[key] == pytest.approx(want[key], rel=1e-9), key
             for key in ("precision", "recall", "density", "coverage"):
                 assert got[key] == want[key], key      # ratios of exact integer counts: identical
+
+
+def test_in_process_devices_equal_one(cuda_device):
+    """AudioMetrics(device_indices=[0, 1]) shape: one process, one host thread, the sweeps sharded over
+    both GPUs by peer copies (dist.evaluate_devices) — same numbers as one device, and the facade
+    routes through it."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from audio_metrics_b200 import AudioMetrics, AudioMetricsData
+    from audio_metrics_b200.dist import evaluate_containers, evaluate_devices
+    from audio_metrics_b200.synth import make_sets_numpy
+
+    ref, cand = make_sets_numpy(5000, 4300, 256, seed=19)
+    R, C = AudioMetricsData(True), AudioMetricsData(True)
+    R.add(torch.from_numpy(ref)); C.add(torch.from_numpy(cand))
+    want = evaluate_containers(R, C, ("fad", "kd", "prdc"), nearest_k=5)
+    R2, C2 = AudioMetricsData(True), AudioMetricsData(True)
+    R2.add(torch.from_numpy(ref)); C2.add(torch.from_numpy(cand))
+    got = evaluate_devices(R2, C2, [0, 1], ("fad", "kd", "prdc"), nearest_k=5)
+    assert got == want
+    # a second evaluation against the same reference reuses its replica and radii on both devices
+    C3 = AudioMetricsData(True); C3.add(torch.from_numpy(cand[:3000]))
+    got3 = evaluate_devices(R2, C3, [0, 1], ("prdc",), nearest_k=5)
+    C4 = AudioMetricsData(True); C4.add(torch.from_numpy(cand[:3000]))
+    assert got3 == evaluate_containers(R, C4, ("prdc",), nearest_k=5)
+    import test_gpu_api as api
+    rng = np.random.default_rng(1)
+    n = 5 * 16000
+    audio_ref, audio_cand = rng.standard_normal((120, n, 2)), rng.standard_normal((100, n, 2))
+    res = []
+    for idx in ([0], [0, 1]):
+        am = AudioMetrics(embedder=api.RandomEmbedder(), mix_function=api.mix_func, metrics=["fad", "kd", "prdc"],
+                          device_indices=idx)
+        am.add_reference(audio_ref)
+        res.append(am.evaluate(audio_cand))
+    assert res[0] == res[1]

@@ -97,6 +97,38 @@ def test_stats_streaming_equals_single_shot(cuda_device):
     assert d.n == 2 * 1101
 
 
+def test_masked_streaming_moments(cuda_device):
+    """The pipeline's per-category accumulation (embed.py:226-236) as one masked launch per batch:
+    equal to adding the selected rows, for containers with and without an embedding store; deferred
+    statistics equal the single-shot ones to round-off (Chan-equivalent, 1e-9)."""
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((3000, 70)) * 0.4 + rng.standard_normal(70)).astype(np.float32)
+    cat = rng.integers(1, 4, size=3000).astype(np.int32)
+    xd, cd = torch.from_numpy(x).cuda(), torch.from_numpy(cat).cuda()
+    for store in (False, True):
+        a = AudioMetricsData(store_embeddings=store)
+        for i in range(0, 3000, 32):
+            sl = slice(i, i + 32)
+            a.add_masked(xd[sl], cd[sl], 2, int((cat[sl] == 2).sum()))
+        sel = x[cat == 2]
+        m_ref, c_ref = _stats64(sel)
+        assert a.n == len(sel)
+        np.testing.assert_allclose(a.mean.cpu().numpy(), m_ref, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(a.cov.cpu().numpy(), c_ref, rtol=1e-9, atol=1e-12)
+        if store:
+            assert torch.equal(a.embeddings.cpu(), torch.from_numpy(sel))
+    # (1, 1) covariance quirk of recompute_stats with one row, on the incoming side of a merge (data.py:56)
+    one = AudioMetricsData(True); one.add(torch.from_numpy(x[:1])); one.recompute_stats()
+    assert tuple(one.cov.shape) == (1, 1)
+    big = AudioMetricsData(True); big.add(torch.from_numpy(x[1:200]))
+    big += one
+    m_ref, c_ref = _stats64(x[:200])
+    assert big.n == 200
+    np.testing.assert_allclose(big.cov.cpu().numpy(), c_ref, rtol=1e-9, atol=1e-12)
+    both = big + big
+    assert both.n == 400 and both.embeddings.shape == (400, 70)
+
+
 # ------------------------------------------------------------------------ FAD
 @pytest.mark.parametrize("n,m,d", [(2000, 2000, 64), (100, 100, 128), (3000, 2500, 512), (50, 80, 33)])
 def test_fad_matches_oracle(cuda_device, n, m, d):
