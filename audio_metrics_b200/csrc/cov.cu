@@ -79,71 +79,82 @@ gram_tile_kernel(const T* __restrict__ X, long long n, int d, long long ld, int 
 // thousand rows): ONE launch that adds the batch's raw moments straight into the running
 // accumulators — sum[d] += column sums, gram[d][d] += X^T X (both triangles) — optionally of only
 // the rows whose category matches (mask[row] == mask_value: the pipeline's per-category boolean
-// mask, applied while loading instead of by an index_select beforehand).  One CTA per 128 x 128 tile
+// mask, applied while loading instead of by an index_select beforehand).  One CTA per 64 x 64 tile
 // on or above the diagonal; every output element has exactly one writer, so the accumulation is
 // deterministic without atomics.  The reference finalises and Chan-merges a d x d covariance per
 // batch (data.py:37-47,77-94); here nothing is finalised until the statistics are read.
+constexpr int kST = 64;   // tile edge of the small-batch kernel: 36 CTAs at d = 512 (the batch is tiny, spread the d x d update)
 template <typename T>
 __global__ void __launch_bounds__(256)
 moments_small_kernel(const T* __restrict__ X, long long n, int d, long long ld, const int32_t* __restrict__ mask,
                      int mask_value, int nt, double* __restrict__ sum, double* __restrict__ gram) {
-  __shared__ __align__(16) double As[kGK][kGT];
-  __shared__ __align__(16) double Bs[kGK][kGT];
+  // the operand stages and, after the k loop, the transposed tile of the mirrored update share one buffer
+  __shared__ __align__(16) double buf[kST * (kST + 1)];
+  double (*As)[kST] = reinterpret_cast<double (*)[kST]>(buf);
+  double (*Bs)[kST] = reinterpret_cast<double (*)[kST]>(buf + kGK * kST);
+  double (*Tr)[kST + 1] = reinterpret_cast<double (*)[kST + 1]>(buf);
   int tp = blockIdx.x, ti = 0;
   while (tp >= nt - ti) { tp -= nt - ti; ++ti; }
   const int tj = ti + tp;
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
-  double acc[8][8];
+  double acc[4][4];
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
-  double csum = 0.0;   // threads 0..127 of a diagonal tile: column sum of column ti*128 + tid
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  double csum = 0.0;   // threads 0..63 of a diagonal tile: column sum of column ti*64 + tid
   for (long long r = 0; r < n; r += kGK) {
-    for (int e = tid; e < kGK * kGT; e += 256) {
-      const int rr = e / kGT, cc = e % kGT;
+    for (int e = tid; e < kGK * kST; e += 256) {
+      const int rr = e / kST, cc = e % kST;
       const long long row = r + rr;
       const bool live = row < n && (mask == nullptr || mask[row] == mask_value);
-      const int ca = ti * kGT + cc, cb = tj * kGT + cc;
+      const int ca = ti * kST + cc, cb = tj * kST + cc;
       As[rr][cc] = (live && ca < d) ? static_cast<double>(X[row * ld + ca]) : 0.0;
       Bs[rr][cc] = (live && cb < d) ? static_cast<double>(X[row * ld + cb]) : 0.0;
     }
     __syncthreads();
-    if (ti == tj && tid < kGT) {
+    if (ti == tj && tid < kST) {
 #pragma unroll
       for (int kk = 0; kk < kGK; ++kk) csum += As[kk][tid];
     }
 #pragma unroll
     for (int kk = 0; kk < kGK; ++kk) {
-      double a[8], b[8];
+      const double2 a0 = *reinterpret_cast<const double2*>(&As[kk][ty * 4]);
+      const double2 a1 = *reinterpret_cast<const double2*>(&As[kk][ty * 4 + 2]);
+      const double2 b0 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4]);
+      const double2 b1 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4 + 2]);
+      const double a[4] = {a0.x, a0.y, a1.x, a1.y};
+      const double b[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
-      for (int v = 0; v < 8; v += 2) {
-        const double2 av = *reinterpret_cast<const double2*>(&As[kk][ty * 8 + v]);
-        const double2 bv = *reinterpret_cast<const double2*>(&Bs[kk][tx * 8 + v]);
-        a[v] = av.x; a[v + 1] = av.y;
-        b[v] = bv.x; b[v + 1] = bv.y;
-      }
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int gi = ti * kGT + ty * 8 + i;
-    if (gi >= d) continue;
+  for (int i = 0; i < 4; ++i) {
+    const int gi = ti * kST + ty * 4 + i;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int gj = tj * kGT + tx * 8 + j;
-      if (gj >= d) continue;
-      gram[static_cast<long long>(gi) * d + gj] += acc[i][j];
-      if (ti != tj) gram[static_cast<long long>(gj) * d + gi] += acc[i][j];   // mirror of an off-diagonal tile
+    for (int j = 0; j < 4; ++j) {
+      const int gj = tj * kST + tx * 4 + j;
+      if (gi < d && gj < d) gram[static_cast<long long>(gi) * d + gj] += acc[i][j];
     }
   }
-  if (ti == tj && tid < kGT && ti * kGT + tid < d) sum[ti * kGT + tid] += csum;
+  if (ti != tj) {   // mirror of an off-diagonal tile, written row-wise (the k loop ended on a barrier)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Tr[tx * 4 + j][ty * 4 + i] = acc[i][j];
+    __syncthreads();
+    for (int e = tid; e < kST * kST; e += 256) {
+      const int rr = e / kST, cc = e % kST;
+      const int gi = tj * kST + rr, gj = ti * kST + cc;
+      if (gi < d && gj < d) gram[static_cast<long long>(gi) * d + gj] += Tr[rr][cc];
+    }
+  }
+  if (ti == tj && tid < kST && ti * kST + tid < d) sum[ti * kST + tid] += csum;
 }
 
 // gram[i][j] += sum over slabs of the upper-tile partials, mirrored to the lower
@@ -299,7 +310,7 @@ int amb_cov_accumulate_masked(int dev, amb_stream_t stream, const void* X, int d
   DeviceGuard guard(dev);
   if (!guard.ok) return AMB_ERR_CUDA;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int nt = (d + kGT - 1) / kGT;
+  const int nt = (d + kST - 1) / kST;
   const unsigned grid = static_cast<unsigned>(nt * (nt + 1) / 2);
   if (dtype == AMB_F32)
     moments_small_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(X), n, d, ld, mask, mask_value, nt, sum, gram);

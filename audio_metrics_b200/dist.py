@@ -50,16 +50,82 @@ def _world(group):
     return 1, 0
 
 
-def _allgather_rows(x: torch.Tensor, n: int, chunk: int, group):
-    """Gather equally padded row shards and cut the result back to n rows."""
+def _allgather_rows(x: torch.Tensor, counts, group):
+    """All ranks' row blocks, concatenated in rank order.  ``counts[r]`` = rows rank r contributes
+    (any sizes: who holds which rows is the caller's business, e.g. wherever the embedder left them).
+    One NCCL allgather of blocks padded to the largest; when only the last block is short (the
+    regular case) the result is a view of the receive buffer, otherwise one compaction copy."""
     world, _ = _world(group)
     if world == 1:
-        return x[:n]
-    pad = torch.zeros((chunk,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    pad[: x.shape[0]] = x
-    out = torch.empty((world * chunk,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        return x
+    maxc = max(max(counts), 1)
+    if x.shape[0] == maxc and x.is_contiguous():
+        pad = x
+    else:
+        pad = torch.zeros((maxc,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        pad[: x.shape[0]] = x
+    out = torch.empty((world * maxc,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     dist.all_gather_into_tensor(out, pad, group=group)
-    return out[:n]
+    if all(c == maxc for c in counts[:-1]):
+        return out[: sum(counts)]
+    return torch.cat([out[r * maxc: r * maxc + counts[r]] for r in range(world)])
+
+
+def _allgather_counts(n_local: int, device, group):
+    """Rows held by every rank (python ints): one tiny collective."""
+    world, _ = _world(group)
+    if world == 1:
+        return [n_local]
+    t = torch.zeros(world, dtype=torch.int64, device=device)
+    mine = torch.tensor([n_local], dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(t, mine, group=group)
+    return [int(v) for v in t.tolist()]
+
+
+# ---- work partition.  After the allgather every rank holds ALL rows, so which rows a rank SWEEPS is
+# independent of which rows it contributed.  The Frechet distance is N-independent work (pivoted
+# Cholesky + 69 fp64 GEMMs of d^3: 3.8 ms at d = 512 on a B200) that only one rank needs to do; that
+# rank gets a proportionally smaller share of the all-pairs sweeps so that all ranks finish together.
+FAD_RANK = 0
+
+
+def fad_seconds(d: int) -> float:
+    """Measured cost model of amb_frechet on a B200 (profiles/r02_*): latency-bound pivoted Cholesky
+    (~d steps), 69 GEMMs (launch-bound below d ~ 256, d^3 above), fixed glue."""
+    dp = -(-d // 64) * 64
+    return 1e-3 * (0.7 + 1.4 * (d / 512.0) + 1.7 * max((dp / 512.0) ** 3, 0.05))
+
+
+def sweep_seconds(n_ref: int, n_cand: int, d: int) -> float:
+    """The three all-pairs sweeps on one B200: 1.25e12 pairs/s at d = 512 (power-capped tensor pipe),
+    proportional to the padded width."""
+    kb = -(-d // 32)
+    return (float(n_ref) * n_ref + float(n_cand) * n_cand + float(n_ref) * n_cand) * (kb / 16.0) / 1.25e12
+
+
+def work_weights(world: int, n_ref: int, n_cand: int, d: int, with_fad: bool):
+    """Relative share of the sweeps per rank: equal, except that the rank that also computes the
+    Frechet distance takes less.  With W the sweep time of the whole problem on one GPU and F the
+    FAD time, all ranks finish together at (W + F) / world when rank FAD_RANK sweeps the fraction
+    1 / world - F / W ... i.e. a weight of 1 - world F / (W + F) relative to the others."""
+    w = [1.0] * world
+    if world > 1 and with_fad:
+        W, F = sweep_seconds(n_ref, n_cand, d), fad_seconds(d)
+        w[FAD_RANK] = min(1.0, max(0.25, 1.0 - world * F / (W + F)))
+    return w
+
+
+def work_rows(n: int, weights, rank: int):
+    """(row0, nrows) of the rows ``rank`` sweeps: boundaries at the weighted quantiles of [0, n),
+    rounded to ROW_ALIGN (the CTA-pair engine takes row tiles two at a time)."""
+    total = sum(weights)
+    def bound(r):
+        if r >= len(weights):
+            return n
+        b = int(round(n * sum(weights[:r]) / total / ROW_ALIGN)) * ROW_ALIGN
+        return min(b, n)
+    b0, b1 = bound(rank), bound(rank + 1)
+    return b0, max(0, b1 - b0)
 
 
 def _allreduce(t: torch.Tensor, group, op=None):
@@ -239,6 +305,9 @@ class _Held:
     def full_container(self, gathered):
         return self.ops.container(gathered)
 
+    def n_local(self):
+        return 0 if self.empty else (self.c.n or 0)
+
     def stats(self):
         """(mean, cov) of the rows held here — final on one GPU, no moment exchange needed."""
         mean, cov = self.c.mean, self.c.cov
@@ -260,25 +329,30 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
     k = nearest_k if nearest_k is not None else max(1, min(10, n_ref, n_cand))   # audio_metrics.py:263
     d = ref.d if ref is not None else None
 
-    def full(s, n):
-        """(container over ALL rows of the set, this rank's row range) — gathered once per set."""
+    with_fad = bool(want_fad or extra_fad)
+    weights = work_weights(world, n_ref, n_cand, d, with_fad) if ref is not None else [1.0] * world
+
+    def full(s):
+        """Container over ALL rows of the set — gathered once per set (cached with the set)."""
         if world == 1 and isinstance(s, _Held):
-            return s.c, 0, n, n              # the container itself (never cached inside itself: no cycles)
+            return s.c                       # the container itself (never cached inside itself: no cycles)
         key = ("full", world, id(group))
         hit = s.cache.get(key)
         if hit is None:
-            row0, nrows, chunk = shard_rows(n, world, rank)
             rows = s.rows()
-            assert rows.shape[0] == nrows, "shards must follow shard_rows()"
-            hit = s.cache[key] = (s.full_container(_allgather_rows(rows, n, chunk, group)), row0, nrows, chunk)
+            counts = _allgather_counts(rows.shape[0], rows.device, group)
+            assert sum(counts) == s.n_total, "row counts of the ranks do not add up to the set size"
+            hit = s.cache[key] = s.full_container(_allgather_rows(rows, counts, group))
         return hit
 
     def radii(s, n):
-        c, row0, nrows, chunk = full(s, n)
+        c = full(s)
         key = f"radii_{k}"
         r = c.radii.get(key)
         if r is None:
-            r = _allgather_rows(ops.radii_rows(c, row0, nrows, k), n, chunk, group).contiguous()
+            row0, nrows = work_rows(n, weights, rank)
+            counts = [work_rows(n, weights, q)[1] for q in range(world)]
+            r = _allgather_rows(ops.radii_rows(c, row0, nrows, k), counts, group).contiguous()
             c.radii[key] = r
         return r
 
@@ -316,12 +390,18 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
                 off += sz
             pending["_mom"] = mom
         lookup = lambda s: stats[[t is s for t in stat_sets].index(True)]
-        pending["fad"] = ops.frechet_batch([(lookup(x), lookup(y)) for _, x, y in fad_pairs])
+        if world == 1 or rank == FAD_RANK:
+            pending["fad"] = ops.frechet_batch([(lookup(x), lookup(y)) for _, x, y in fad_pairs])
+        else:   # N-independent work: one rank computes it (and sweeps fewer rows, work_weights), all receive it
+            pending["fad"] = torch.zeros(len(fad_pairs), dtype=torch.float64, device=mom.device)
+        if world > 1:
+            dist.broadcast(pending["fad"], src=dist.get_global_rank(group, FAD_RANK) if group is not None else FAD_RANK,
+                           group=group)
 
     # ---- PRDC
     def counts(list_cap):
-        cref, r_row0, r_nrows, _ = full(ref, n_ref)
-        ccand = full(cand, n_cand)[0]
+        cref, ccand = full(ref), full(cand)
+        r_row0, r_nrows = work_rows(n_ref, weights, rank)
         col, t, unc = ops.count_rows(cref, ccand, r_ref, r_cand, r_row0, r_nrows, k, list_cap=list_cap)
         _allreduce(col, group)                                  # [m] int32
         _allreduce(t, group)                                    # 2 int64
@@ -341,7 +421,7 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
         idx = kd_subset_indices(n_cand, n_ref, m, kd_subsets, kd_seed)           # features_1 = candidate
         mine = idx[rank::world]
         per = -(-kd_subsets // world)
-        f1, f2 = full(cand, n_cand)[0].embeddings, full(ref, n_ref)[0].embeddings
+        f1, f2 = full(cand).embeddings, full(ref).embeddings
         local = ops.kd_mmds(f1, f2, mine, 1.0 / d, KID_COEF0, KID_DEGREE,
                             key=(n_cand, n_ref, m, kd_subsets, kd_seed, rank, world))
         if world > 1:
@@ -382,7 +462,8 @@ def evaluate_sharded(ref_shard, cand_shard, n_ref, n_cand, metrics=("fad", "kd",
                      group=None, ops=None, kd_subsets=100, kd_subset_size=1000, kd_seed=1234, ready=None):
     """FAD / KD / PRDC of (reference, candidate) given this rank's row shards.
 
-    ``ref_shard`` / ``cand_shard`` are this rank's rows per ``shard_rows``; every
+    ``ref_shard`` / ``cand_shard`` are the rows this rank holds — in rank order they make up the
+    sets; ``shard_rows`` gives an even split, but any sizes are accepted.  Every
     rank returns the same result dict (keys as AudioMetrics.evaluate,
     audio_metrics.py:254-274).  With an uninitialised process group this is the
     single-GPU path.
@@ -395,9 +476,6 @@ def evaluate_sharded(ref_shard, cand_shard, n_ref, n_cand, metrics=("fad", "kd",
     shard is first touched.
     """
     ops = ops or default_ops(ref_shard.device if ref_shard.is_cuda else None)
-    world, rank = _world(group)
-    assert ref_shard.shape[0] == shard_rows(n_ref, world, rank)[1], "shards must follow shard_rows()"
-    assert cand_shard.shape[0] == shard_rows(n_cand, world, rank)[1], "shards must follow shard_rows()"
     ev_ref, ev_cand = ready if ready is not None else (None, None)
     return _fused(ops, _Shard(ref_shard, n_ref, ops, ev_ref), _Shard(cand_shard, n_cand, ops, ev_cand), metrics,
                   nearest_k, group, kd_subsets=kd_subsets, kd_subset_size=kd_subset_size, kd_seed=kd_seed)
@@ -498,7 +576,8 @@ def evaluate_devices(ref, cand, devices, metrics=("fad", "kd", "prdc"), nearest_
                                    kd_subset_size=kd_subset_size, kd_seed=kd_seed)
     n_ref, n_cand = ref.n, cand.n
     k = nearest_k if nearest_k is not None else max(1, min(10, n_ref, n_cand))
-    main0 = torch.cuda.current_stream(dev0)
+    # devices[0] also computes the N-independent metrics: it sweeps fewer rows (work_weights)
+    weights = work_weights(world, n_ref, n_cand, _width(ref), bool(rest) or apa is not None)
 
     # ---- replicate (reference first), then every device sweeps its row shard
     def sweep_radii(c, n):
@@ -507,7 +586,7 @@ def evaluate_devices(ref, cand, devices, metrics=("fad", "kd", "prdc"), nearest_
             return [_replica(c, d).radii.setdefault(key, c.radii[key].to(d, non_blocking=True)) for d in devices]
         parts = []
         for i, d in enumerate(devices):
-            row0, nrows, _ = shard_rows(n, world, i)
+            row0, nrows = work_rows(n, weights, i)
             with torch.cuda.device(d):
                 parts.append(default_ops(d).radii_rows(_replica(c, d), row0, nrows, k))
         full0 = torch.cat([p.to(dev0, non_blocking=True) for p in parts])      # peer copies of [n / world] floats
@@ -525,7 +604,7 @@ def evaluate_devices(ref, cand, devices, metrics=("fad", "kd", "prdc"), nearest_
     def counts(list_cap):
         cols, ts, uncs = [], [], []
         for i, d in enumerate(devices):
-            row0, nrows, _ = shard_rows(n_ref, world, i)
+            row0, nrows = work_rows(n_ref, weights, i)
             with torch.cuda.device(d):
                 col, t, unc = default_ops(d).count_rows(_replica(ref, d), _replica(cand, d), r_ref[i], r_cand[i], row0,
                                                         nrows, k, list_cap=list_cap)
@@ -549,5 +628,4 @@ def evaluate_devices(ref, cand, devices, metrics=("fad", "kd", "prdc"), nearest_
             hits, total, recalled, covered, uncertain, cap = counts(list_cap).tolist()
     result.update(precision=hits / n_cand, recall=recalled / n_ref, density=(1.0 / float(k)) * (total / n_cand),
                   coverage=covered / n_ref)                                        # prdc.py:36-48
-    del main0
     return result

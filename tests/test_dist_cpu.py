@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 
 import oracle
 from oracle.prdc import cdist_exact
-from audio_metrics_b200.dist import evaluate_sharded, shard_rows
+from audio_metrics_b200.dist import evaluate_sharded, shard_rows, work_rows, work_weights
 from audio_metrics_b200.synth import make_sets_numpy
 
 
@@ -30,6 +30,29 @@ def test_shard_rows_cover_and_align():
             assert all(s[1] == s[2] for s in nonempty[:-1])
 
 
+def test_work_partition_covers_and_aligns():
+    """The weighted sweep partition (the rank that also computes the Frechet distance sweeps fewer
+    rows): contiguous, 256-aligned starts, covers [0, n) exactly, equal shares without FAD."""
+    for n_ref, n_cand, d in ((200000, 200000, 512), (1000, 900, 128), (130, 257, 32), (1, 5, 8), (10000, 1000000, 512)):
+        for world in (1, 2, 3, 4, 8):
+            for with_fad in (False, True):
+                w = work_weights(world, n_ref, n_cand, d, with_fad)
+                assert len(w) == world and all(0 < x <= 1 for x in w)
+                if not with_fad or world == 1:
+                    assert w == [1.0] * world
+                else:
+                    assert w[0] <= 1.0 and w[1:] == [1.0] * (world - 1)
+                for n in (n_ref, n_cand):
+                    spans = [work_rows(n, w, r) for r in range(world)]
+                    pos = 0
+                    for row0, nrows in spans:
+                        assert row0 == pos and (row0 % 256 == 0 or nrows == 0) and nrows >= 0
+                        pos += nrows
+                    assert pos == n
+    w = work_weights(8, 200000, 200000, 512, True)
+    assert 0.6 < w[0] < 0.8          # 3.8 ms of FAD against 12 ms of sweeps per rank
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -43,8 +66,12 @@ def _worker(rank, world, port, n_ref, n_cand, d, k, out, overflow=False):
     try:
         from oracle_ops import OracleOps
         ref, cand = make_sets_numpy(n_ref, n_cand, d, seed=77)
-        r0, rn, _ = shard_rows(n_ref, world, rank)
-        c0, cn, _ = shard_rows(n_cand, world, rank)
+        if overflow:     # any row counts per rank are accepted: who holds which rows is the caller's business
+            r0, rn = (0, n_ref // 3) if rank == 0 else (n_ref // 3, n_ref - n_ref // 3)
+            c0, cn = (0, n_cand - 7) if rank == 0 else (n_cand - 7, 7)
+        else:
+            r0, rn, _ = shard_rows(n_ref, world, rank)
+            c0, cn, _ = shard_rows(n_cand, world, rank)
         ops = OracleOps()
         ops.overflow_once = overflow
         res = evaluate_sharded(torch.from_numpy(ref[r0:r0 + rn]), torch.from_numpy(cand[c0:c0 + cn]), n_ref, n_cand,
