@@ -71,15 +71,18 @@ def _allgather_rows(x: torch.Tensor, counts, group):
     return torch.cat([out[r * maxc: r * maxc + counts[r]] for r in range(world)])
 
 
-def _allgather_counts(n_local: int, device, group):
-    """Rows held by every rank (python ints): one tiny collective."""
+def _gather_meta(values, device, group):
+    """Every rank's small list of python ints (row counts, widths): ONE collective and the only
+    host synchronisation of a step besides the final read-back — issued first, before any sweep is
+    queued, so it costs one allgather latency and not a pipeline drain."""
     world, _ = _world(group)
     if world == 1:
-        return [n_local]
-    t = torch.zeros(world, dtype=torch.int64, device=device)
-    mine = torch.tensor([n_local], dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(t, mine, group=group)
-    return [int(v) for v in t.tolist()]
+        return [list(values)]
+    mine = torch.tensor(list(values), dtype=torch.int64, device=device)
+    out = torch.zeros(world * len(values), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    flat = out.tolist()
+    return [flat[r * len(values):(r + 1) * len(values)] for r in range(world)]
 
 
 # ---- work partition.  After the allgather every rank holds ALL rows, so which rows a rank SWEEPS is
@@ -145,6 +148,19 @@ def kd_subset_indices(n1: int, n2: int, m: int, subsets: int, seed: int) -> np.n
     idx = draw_subset_indices(n1, n2, m, subsets, seed)
     idx.setflags(write=False)
     return idx
+
+
+_KD_ORDER = {}
+
+
+def _kd_order(subsets, world, per, device):
+    """Index tensor that puts the round-robin dealt subset values back in subset order (cached: it
+    depends on nothing but the counts)."""
+    key = (subsets, world, per, str(device))
+    t = _KD_ORDER.get(key)
+    if t is None:
+        t = _KD_ORDER[key] = torch.tensor([(s % world) * per + s // world for s in range(subsets)], device=device)
+    return t
 
 
 class CudaOps:
@@ -250,8 +266,9 @@ def default_ops(device=None):
 class _Shard:
     """A row shard handed in as a plain tensor (evaluate_sharded)."""
 
-    def __init__(self, rows, n_total, ops, ready=None):
+    def __init__(self, rows, n_total, ops, ready=None, counts=None):
         self.rows_, self.n_total, self.ops, self.ready = rows, n_total, ops, ready
+        self.counts = counts            # rows held by every rank
         self.cache = {}
         self.d = rows.shape[1]
         self.device = rows.device
@@ -282,8 +299,9 @@ class _Held:
     """A row shard held by an AudioMetricsData (evaluate_containers): statistics come from the
     container, derived data is cached on it and dropped when rows are added."""
 
-    def __init__(self, c, n_total, ops, d=None):
+    def __init__(self, c, n_total, ops, d=None, counts=None):
         self.c, self.n_total, self.ops = c, n_total, ops
+        self.counts = counts            # rows held by every rank
         self.cache = c._cache
         self.empty = not c.n                       # this rank holds no rows of the set (tiny sets, many ranks)
         self.d = _width(c) or d
@@ -304,9 +322,6 @@ class _Held:
 
     def full_container(self, gathered):
         return self.ops.container(gathered)
-
-    def n_local(self):
-        return 0 if self.empty else (self.c.n or 0)
 
     def stats(self):
         """(mean, cov) of the rows held here — final on one GPU, no moment exchange needed."""
@@ -339,10 +354,8 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
         key = ("full", world, id(group))
         hit = s.cache.get(key)
         if hit is None:
-            rows = s.rows()
-            counts = _allgather_counts(rows.shape[0], rows.device, group)
-            assert sum(counts) == s.n_total, "row counts of the ranks do not add up to the set size"
-            hit = s.cache[key] = s.full_container(_allgather_rows(rows, counts, group))
+            assert sum(s.counts) == s.n_total, "row counts of the ranks do not add up to the set size"
+            hit = s.cache[key] = s.full_container(_allgather_rows(s.rows(), s.counts, group))
         return hit
 
     def radii(s, n):
@@ -429,8 +442,7 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
             pad[: local.shape[0]] = local
             allv = torch.empty(world * per, dtype=torch.float64, device=local.device)
             dist.all_gather_into_tensor(allv, pad, group=group)
-            order = torch.tensor([(s % world) * per + s // world for s in range(kd_subsets)], device=local.device)
-            pending["kd"] = allv[order]
+            pending["kd"] = allv[_kd_order(kd_subsets, world, per, local.device)]
         else:
             pending["kd"] = local
 
@@ -477,7 +489,9 @@ def evaluate_sharded(ref_shard, cand_shard, n_ref, n_cand, metrics=("fad", "kd",
     """
     ops = ops or default_ops(ref_shard.device if ref_shard.is_cuda else None)
     ev_ref, ev_cand = ready if ready is not None else (None, None)
-    return _fused(ops, _Shard(ref_shard, n_ref, ops, ev_ref), _Shard(cand_shard, n_cand, ops, ev_cand), metrics,
+    meta = _gather_meta([ref_shard.shape[0], cand_shard.shape[0]], ref_shard.device, group)
+    return _fused(ops, _Shard(ref_shard, n_ref, ops, ev_ref, [m[0] for m in meta]),
+                  _Shard(cand_shard, n_cand, ops, ev_cand, [m[1] for m in meta]), metrics,
                   nearest_k, group, kd_subsets=kd_subsets, kd_subset_size=kd_subset_size, kd_seed=kd_seed)
 
 
@@ -495,16 +509,14 @@ def evaluate_containers(ref, cand, metrics=("fad", "kd", "prdc"), nearest_k=5, g
     ops = default_ops(some.device)
     world, _ = _world(group)
 
-    def sizes(c):
-        """(rows over all ranks, embedding width) — two tiny collectives, once per container state."""
-        if world == 1:
-            return c.n, _width(c)
-        t = torch.tensor([c.n or 0, _width(c) or 0], dtype=torch.int64, device=ops.device)
-        n = t[:1].clone()
-        _allreduce(n, group)
-        _allreduce(t, group, dist.ReduceOp.MAX)
-        return int(n), int(t[1])
-
+    sets = [c for c in (ref, cand) + (tuple(apa[:3]) if apa is not None else ()) if c is not None]
+    key = ("meta", world, id(group))
+    if any(key not in c._cache for c in sets):
+        # rows and width of every set on every rank, in one exchange (cached with each container's state)
+        meta = _gather_meta([v for c in sets for v in (c.n or 0, _width(c) or 0)], ops.device, group)
+        for i, c in enumerate(sets):
+            counts = [m[2 * i] for m in meta]
+            c._cache[key] = (sum(counts), max(m[2 * i + 1] for m in meta), counts)
     views = {}
 
     def held(c):
@@ -512,11 +524,8 @@ def evaluate_containers(ref, cand, metrics=("fad", "kd", "prdc"), nearest_k=5, g
         #  cycle, and its device buffers would then wait for the cyclic garbage collector)
         v = views.get(id(c))
         if v is None:
-            key = ("sizes", world, id(group))
-            if key not in c._cache:
-                c._cache[key] = sizes(c)
-            n_total, d = c._cache[key]
-            v = views[id(c)] = _Held(c, n_total, ops, d)
+            n_total, d, counts = c._cache[key]
+            v = views[id(c)] = _Held(c, n_total, ops, d, counts)
         return v
 
     extra = []
