@@ -82,7 +82,9 @@ def prdc_totals(reference, candidate, nearest_k, row_range=None, ref_radii=None,
         return col_count, rec[:nrows], cov[:nrows], totals
     nbytes = L.amb_prdc_ws_bytes(n, m) if list_cap is None else L.amb_prdc_ws_bytes_cap(n, m, max(1, int(list_cap)))
     ws = _lib.workspace(nbytes, dev)
-    totals[5] = L.amb_prdc_ws_list_cap(n, m, ws.numel())
+    # (fill_ passes the scalar as a kernel argument; `totals[5] = value` would stage it through a
+    #  synchronous host-to-device copy and drain the stream in the middle of the step)
+    totals[5:].fill_(int(L.amb_prdc_ws_list_cap(n, m, ws.numel())))
     _lib.check(L.amb_prdc_counts(dev.index, st, xr.data_ptr(), xr.stride(0), ref.packed().data_ptr(), n,
                                  ref_radii.data_ptr(), xc.data_ptr(), xc.stride(0), cand.packed().data_ptr(), m,
                                  cand_radii.data_ptr(), d, _lib.dtype_code(xr), row0, nrows, col_count.data_ptr(),

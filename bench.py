@@ -309,7 +309,14 @@ def run_b200_arm(args):
     prof = (C.c_double * 4)()
     L.amb_profile_read(prof)   # clear
     launches0 = _lib.launch_count()
-    ms_step, result = timed(lambda: step(ref_shard, cand_shard), args.steps)
+    if os.environ.get("AMB_BENCH_PROFILE") and rank == 0:
+        import cProfile, pstats
+        pr = cProfile.Profile(); pr.enable()
+        ms_step, result = timed(lambda: step(ref_shard, cand_shard), args.steps)
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(28)
+    else:
+        ms_step, result = timed(lambda: step(ref_shard, cand_shard), args.steps)
     launches = _lib.launch_count() - launches0
     L.amb_profile_read(prof)
     L.amb_profile_enable(0)
