@@ -364,7 +364,11 @@ static int pick_kt(int k) {
 //   * Few row tiles: split columns so every SM has work, choosing the split
 //     count with the smallest round-robin makespan in column tiles.
 constexpr long long kCountSplitBytes = 16ll << 20;
-static int pick_split(int dev, long long n_rt, long long n_ct, int kb_count, long long l2_bytes) {
+// `split_cost`: relative cost added per extra split.  The count epilogue is stateless (only the fixed
+// per-item cost of one tile below); the radii epilogue restarts its candidate lists in every split,
+// and the refine kernel merges 2 K candidates per split and row — measured at 200k columns, d = 512
+// (profiles/r02_shard_sweeps.txt): about 7 % of the sweep per extra split.
+static int pick_split(int dev, long long n_rt, long long n_ct, int kb_count, long long l2_bytes, double split_cost = 0.0) {
   const int sms = sm_count(dev);
   int s_min = 1;
   if (l2_bytes > 0) {
@@ -388,7 +392,7 @@ static int pick_split(int dev, long long n_rt, long long n_ct, int kb_count, lon
     const long long rounds = (items + grid - 1) / grid;
     const long long tiles = (n_ct + s - 1) / s;
     // the last round is partial: CTAs that take part in it carry `rounds` items, the rest one fewer
-    const long long span = rounds * (tiles + 1);
+    const long long span = static_cast<long long>(rounds * (tiles + 1) * (1.0 + split_cost * (s - 1)) * 16.0);
     if (best_span < 0 || span < best_span) { best_span = span; best_s = s; }
   }
   return best_s;
@@ -502,7 +506,7 @@ int amb_knn_radii(int dev, amb_stream_t stream, const void* X, int dtype, long l
   PackedPtrs p = packed_ptrs(const_cast<void*>(packed), n, d);
   const long long n_rt = (nrows + kTileM - 1) / kTileM;
   const long long n_ct = p.rows_pad / kTileN;
-  int n_split = pick_split(dev, n_rt, n_ct, p.kb_count, 0);
+  int n_split = pick_split(dev, n_rt, n_ct, p.kb_count, 0, 0.07);
   if (const int v = option(kOptTopkSplit)) {   // tuning knob
     if (v >= 1 && v <= 64 && v <= n_ct) n_split = v;
   }

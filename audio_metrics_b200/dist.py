@@ -150,6 +150,24 @@ def kd_subset_indices(n1: int, n2: int, m: int, subsets: int, seed: int) -> np.n
     return idx
 
 
+TRACE = None     # set to a list to collect (label, CUDA event) marks of the next fused step (diagnostics)
+
+
+def _mark(label, device):
+    if TRACE is not None and device.type == "cuda":
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(device))
+        TRACE.append((label, ev))
+
+
+def trace_report():
+    """[(label, ms since the previous mark)] of the marks collected in TRACE (synchronises)."""
+    if not TRACE:
+        return []
+    torch.cuda.synchronize()
+    return [(b[0], a[1].elapsed_time(b[1])) for a, b in zip(TRACE[:-1], TRACE[1:])]
+
+
 _KD_ORDER = {}
 
 
@@ -381,15 +399,24 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
                 stat_sets.append(s)
     stat_sets.sort(key=lambda s: s is cand)                     # the candidate's moments last
     local_stats = world == 1 and all(isinstance(s, _Held) for s in stat_sets)   # statistics are already final
+    tdev = (ref if ref is not None else stat_sets[0]).device
+    _mark("start", tdev)
     moms = []
     done_ref_sweep = False
     for s in stat_sets:
         if s is cand and want_prdc and not done_ref_sweep:
+            _mark("moments (reference)", tdev)
+            full(ref)
+            _mark("allgather reference", tdev)
+            full(ref).packed() if hasattr(full(ref), "packed") else None
+            _mark("pack reference", tdev)
             r_ref = radii(ref, n_ref)
+            _mark("radii reference (sweep, refine, allgather)", tdev)
             done_ref_sweep = True
         moms.append(s.stats() if local_stats else s.moments())
     if want_prdc and not done_ref_sweep:
         r_ref = radii(ref, n_ref)
+    _mark("moments", tdev)
     if fad_pairs:
         if local_stats:
             stats = moms
@@ -410,6 +437,7 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
         if world > 1:
             dist.broadcast(pending["fad"], src=dist.get_global_rank(group, FAD_RANK) if group is not None else FAD_RANK,
                            group=group)
+        _mark("allreduce moments, Frechet distances" + ("" if world == 1 or rank == FAD_RANK else " (received)"), tdev)
 
     # ---- PRDC
     def counts(list_cap):
@@ -424,8 +452,14 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
                           t.to(torch.int64), unc.to(torch.int64)])
 
     if want_prdc:
+        full(cand)
+        _mark("allgather candidate", tdev)
+        full(cand).packed() if hasattr(full(cand), "packed") else None
+        _mark("pack candidate", tdev)
         r_cand = radii(cand, n_cand)
+        _mark("radii candidate (sweep, refine, allgather)", tdev)
         pending["prdc"] = counts(None)
+        _mark("counts (sweep, refine, allreduce)", tdev)
 
     # ---- KD: subsets dealt round-robin to the ranks
     if want_kd:
@@ -445,6 +479,7 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
             pending["kd"] = allv[_kd_order(kd_subsets, world, per, local.device)]
         else:
             pending["kd"] = local
+        _mark("kernel distance", tdev)
 
     # ---- the one read-back
     result = {}

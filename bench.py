@@ -381,6 +381,18 @@ def run_b200_arm(args):
                              "inputs from pageable host memory: 3 x the input bytes cross PCIe)",
                     "result": res_cabi}
 
+    # ---- where the time of one step goes on this rank and on the last one (CUDA events between phases)
+    from audio_metrics_b200 import dist as amb_dist
+    amb_dist.TRACE = []
+    step(ref_shard, cand_shard)
+    mine = amb_dist.trace_report()
+    amb_dist.TRACE = None
+    phase_trace = {"rank 0": {k: round(v, 3) for k, v in mine}}
+    if world > 1:
+        box = [None] * world
+        dist.all_gather_object(box, [(k, round(v, 3)) for k, v in mine])
+        phase_trace[f"rank {world - 1}"] = dict(box[-1])
+
     # ---- per-phase latency (FAD latency is part of the headline)
     phases = {}
     for name in ("fad", "kd", "prdc"):
@@ -428,7 +440,7 @@ def run_b200_arm(args):
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "phases_ms": phases, "result": result, "parity": parity_record(result, result_e2e),
+        "phases_ms": phases, "phase_trace_ms": phase_trace, "result": result, "parity": parity_record(result, result_e2e),
         "pairs_per_step": pairs,
     }
     if e2e_cabi is not None:
