@@ -150,6 +150,18 @@ def kd_subset_indices(n1: int, n2: int, m: int, subsets: int, seed: int) -> np.n
     return idx
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One side stream per device for the life of the process (the Frechet distance of the rank that
+    owns it runs there, in the gaps its smaller sweep share leaves before each collective)."""
+    st = _SIDE_STREAMS.get(device.index)
+    if st is None:
+        st = _SIDE_STREAMS[device.index] = torch.cuda.Stream(device)
+    return st
+
+
 TRACE = None     # set to a list to collect (label, CUDA event) marks of the next fused step (diagnostics)
 
 
@@ -397,14 +409,18 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
         for s in (y, x):                                        # references before candidates
             if all(s is not t for t in stat_sets):
                 stat_sets.append(s)
-    stat_sets.sort(key=lambda s: s is cand)                     # the candidate's moments last
+    # One GPU: the candidate's moments last, after the reference sweep (its host-to-device copy may
+    # still be in flight).  Several ranks: all moments first, so that the Frechet distance can start
+    # on its side stream before the first sweep.
+    stat_sets.sort(key=lambda s: s is cand)
+    early_stats = world > 1
     local_stats = world == 1 and all(isinstance(s, _Held) for s in stat_sets)   # statistics are already final
     tdev = (ref if ref is not None else stat_sets[0]).device
     _mark("start", tdev)
     moms = []
     done_ref_sweep = False
     for s in stat_sets:
-        if s is cand and want_prdc and not done_ref_sweep:
+        if s is cand and want_prdc and not done_ref_sweep and not early_stats:
             _mark("moments (reference)", tdev)
             full(ref)
             _mark("allgather reference", tdev)
@@ -414,8 +430,6 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
             _mark("radii reference (sweep, refine, allgather)", tdev)
             done_ref_sweep = True
         moms.append(s.stats() if local_stats else s.moments())
-    if want_prdc and not done_ref_sweep:
-        r_ref = radii(ref, n_ref)
     _mark("moments", tdev)
     if fad_pairs:
         if local_stats:
@@ -430,14 +444,33 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
                 off += sz
             pending["_mom"] = mom
         lookup = lambda s: stats[[t is s for t in stat_sets].index(True)]
-        if world == 1 or rank == FAD_RANK:
-            pending["fad"] = ops.frechet_batch([(lookup(x), lookup(y)) for _, x, y in fad_pairs])
-        else:   # N-independent work: one rank computes it (and sweeps fewer rows, work_weights), all receive it
+        pairs = [(lookup(x), lookup(y)) for _, x, y in fad_pairs]
+        if world == 1:
+            pending["fad"] = ops.frechet_batch(pairs)
+        elif rank == FAD_RANK:
+            # N-independent work: ONE rank computes it.  That rank sweeps fewer rows (work_weights), so it
+            # reaches every collective of the sweeps early; the Frechet kernels run on a side stream and
+            # fill exactly those waits instead of holding all ranks up at the next collective.
+            if mom.is_cuda:
+                side = _side_stream(mom.device)
+                side.wait_stream(torch.cuda.current_stream(mom.device))
+                with torch.cuda.stream(side):
+                    pending["fad"] = ops.frechet_batch(pairs)
+                pending["_fad_side"] = side
+            else:
+                pending["fad"] = ops.frechet_batch(pairs)
+            pending["_fad_inputs"] = stats       # alive until the side stream is joined
+        else:
             pending["fad"] = torch.zeros(len(fad_pairs), dtype=torch.float64, device=mom.device)
-        if world > 1:
-            dist.broadcast(pending["fad"], src=dist.get_global_rank(group, FAD_RANK) if group is not None else FAD_RANK,
-                           group=group)
-        _mark("allreduce moments, Frechet distances" + ("" if world == 1 or rank == FAD_RANK else " (received)"), tdev)
+        _mark("allreduce moments" + (", Frechet distances" if world == 1 else ""), tdev)
+
+    if want_prdc and not done_ref_sweep:
+        full(ref)
+        _mark("allgather reference", tdev)
+        full(ref).packed() if hasattr(full(ref), "packed") else None
+        _mark("pack reference", tdev)
+        r_ref = radii(ref, n_ref)
+        _mark("radii reference (sweep, refine, allgather)", tdev)
 
     # ---- PRDC
     def counts(list_cap):
@@ -483,6 +516,12 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
 
     # ---- the one read-back
     result = {}
+    if fad_pairs and world > 1:
+        if "_fad_side" in pending:
+            torch.cuda.current_stream(pending["fad"].device).wait_stream(pending["_fad_side"])
+        dist.broadcast(pending["fad"], src=dist.get_global_rank(group, FAD_RANK) if group is not None else FAD_RANK,
+                       group=group)
+        _mark("Frechet distances joined, broadcast", tdev)
     if fad_pairs:
         vals = pending["fad"].tolist()
         for (name, _, _), v in zip(fad_pairs, vals):
