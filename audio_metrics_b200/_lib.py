@@ -10,7 +10,10 @@ from pathlib import Path
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "libamb200.so"
+import os as _os
+
+# (AMB200_LIB: an alternative build of the same ABI, for A/B timing of kernel variants on one box)
+_LIB_PATH = Path(_os.environ.get("AMB200_LIB") or Path(__file__).resolve().parent / "libamb200.so")
 _lib = None
 
 AMB_F32, AMB_F64 = 0, 1
