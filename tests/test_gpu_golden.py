@@ -137,3 +137,24 @@ def test_kd_estimators_match_reference(cuda_device):
         for unit in (False, True):
             assert mmd2(kxx, kxy, kyy, unit_diagonal=unit, mmd_est=est) == pytest.approx(
                 oracle.mmd2(kxx, kxy, kyy, unit_diagonal=unit, mmd_est=est), rel=1e-12, abs=1e-15)
+
+
+def test_cuda_c3_golden(cuda_device):
+    """BASELINE config 3 at its stated size: APA on 10k mix / stem pairs (d = 512) with FAD on the
+    stems, against the unmodified reference; north-star tolerance 1e-5 on every Frechet distance."""
+    import json
+    from pathlib import Path
+
+    from audio_metrics_b200.metrics.apa import apa_compute_d_x_xp
+    from audio_metrics_b200.synth import make_apa_sets_numpy
+
+    g = json.loads((Path(__file__).parent / "golden" / "golden_c3.json").read_text())
+    s = make_apa_sets_numpy(g["n"], g["d"], seed=g["seed"])
+    cand, refa, anti = (_amd(s[k], False) for k in ("cand_aligned", "ref_aligned", "ref_misaligned"))
+    assert frechet_distance(cand, refa) == pytest.approx(g["d_y_x"], rel=1e-5)
+    assert frechet_distance(cand, anti) == pytest.approx(g["d_y_xp"], rel=1e-5)
+    d_x_xp = apa_compute_d_x_xp(refa, anti)
+    assert d_x_xp == pytest.approx(g["d_x_xp"], rel=1e-5)
+    assert apa(cand, refa, anti) == pytest.approx(g["apa"], rel=1e-4)          # a ratio of differences of FADs
+    assert apa(cand, refa, anti, d_x_xp) == pytest.approx(g["apa"], rel=1e-4)
+    assert frechet_distance(_amd(s["cand_stems"], False), _amd(s["ref_stems"], False)) == pytest.approx(g["fad_stems"], rel=1e-5)

@@ -168,3 +168,24 @@ def test_mmd2_estimators_match_reference_goldens():
         np.testing.assert_allclose(got64["mmds"], v["reference_f64"]["mmds"], rtol=1e-9, atol=1e-15)
         got32 = oracle.kernel_distance(cand, ref, **args)
         np.testing.assert_allclose(got32["mmds"], v["reference_f32"]["mmds"], rtol=5e-3, atol=2e-7)
+
+
+def test_oracle_c3_golden():
+    """BASELINE config 3 at its stated size (10k mix / stem pairs, d = 512): the oracle's FAD and APA
+    against the unmodified reference (tests/golden/make_golden_c3.py)."""
+    import hashlib
+    import json
+    from pathlib import Path
+
+    from audio_metrics_b200.synth import make_apa_sets_numpy
+
+    g = json.loads((Path(__file__).parent / "golden" / "golden_c3.json").read_text())
+    s = make_apa_sets_numpy(g["n"], g["d"], seed=g["seed"])
+    assert hashlib.sha256(np.ascontiguousarray(np.concatenate([s[k] for k in sorted(s)])).tobytes()).hexdigest() == g["sha256"]
+    f64 = np.dtype(np.float64)
+    st = {k: oracle.batch_stats(v)[:2] for k, v in s.items()}             # reference arithmetic: input dtype, then fp64
+    fad = lambda a, b: oracle.frechet_from_stats(*st[a], *st[b])
+    assert fad("cand_aligned", "ref_aligned") == pytest.approx(g["d_y_x"], rel=1e-6)
+    assert fad("ref_aligned", "ref_misaligned") == pytest.approx(g["d_x_xp"], rel=1e-6)
+    assert fad("cand_stems", "ref_stems") == pytest.approx(g["fad_stems"], rel=1e-6)
+    assert oracle.apa(st["cand_aligned"], st["ref_aligned"], st["ref_misaligned"]) == pytest.approx(g["apa"], rel=1e-5)
