@@ -38,7 +38,8 @@ constexpr int kSyrkStageBytes = kDigits * kSliceChunk + kDigits * (kSliceChunk /
 constexpr int kSyrkThreads = 192;
 constexpr int kQBits = 30;                    // |q| <= 2^30
 constexpr int kMaxKbPerItem = 512;            // 512*64 samples * 49152 (largest class per sample) < 2^31
-constexpr long long kChunkRows = 131072;      // samples per pass (bounds the digit-plane workspace)
+constexpr long long kChunkRows = 262144;      // samples per pass (bounds the digit-plane workspace: 4 B per element);
+                                              // a 200k-row set is one pass: one slice, one SYRK, one reduce launch
 
 // ------------------------------------------------------------------ column scale
 __global__ void __launch_bounds__(256)

@@ -262,9 +262,8 @@ pchol_kernel(double* __restrict__ A, double* __restrict__ Lt, int d, int n_mat, 
   double* Lp = sm;                      // [PB][d]
   double* dg = sm + static_cast<size_t>(PB) * d;   // [d] residual diagonal (-inf: used)
   __shared__ double red_v[16];
-  __shared__ int red_i[16];
-  __shared__ int s_p;
-  __shared__ double s_piv;
+  __shared__ unsigned long long red_key[32];   // [step parity][warp]
+  __shared__ double red_val[32];
   cg::grid_group grid = cg::this_grid();
   const int mat = blockIdx.x / C, c = blockIdx.x % C;
   const bool leader = c == 0;
@@ -296,48 +295,62 @@ pchol_kernel(double* __restrict__ A, double* __restrict__ Lt, int d, int n_mat, 
     if (leader) {
       int npan = 0;
       if (!finished) {
+        // ONE block barrier per pivot step (three before, at 2.5 us per step the dominant cost of the
+        // factorisation).  The arg max travels as a 64-bit key — the bits of the residual diagonal with
+        // the index in the 11 lowest mantissa bits, so the choice of pivot may be off by 2^-42 — reduced
+        // by warp shuffles; the lane that held a warp's best also publishes its exact value, and every
+        // thread scans the 16 warp results itself.  The result arrays are double-buffered by step
+        // parity, so the writes of step jj + 1 cannot overtake a slow reader of step jj; the column and
+        // diagonal writes of step jj are ordered before their readers in step jj + 1 by the same barrier.
         for (int jj = 0; jj < PB && j0 + jj < d; ++jj) {
-          // ---- pivot: arg max of the residual diagonal over unused indices
-          double bv = NEG;
-          int bi = -1;
+          unsigned long long key = 0ull;
+          double val = NEG;
           for (int i = tid; i < d; i += blockDim.x) {
             const double v = dg[i];
-            if (v > bv) { bv = v; bi = i; }
+            const unsigned long long kb =
+                v > 0.0 ? ((static_cast<unsigned long long>(__double_as_longlong(v)) & ~0x7ffull) | static_cast<unsigned>(i)) : 0ull;
+            if (kb > key) { key = kb; val = v; }
           }
+          const unsigned long long mine = key;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi >= 0 && (bi < 0 || oi < bi))) { bv = ov; bi = oi; }
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
+            key = ok > key ? ok : key;
           }
-          if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+          unsigned long long* red_k = red_key + (jj & 1) * 16;
+          double* red_d = red_val + (jj & 1) * 16;
+          if (lane == 0) red_k[warp] = key;
+          if (mine == key && key != 0ull) red_d[warp] = val;     // unique: the index is part of the key
           __syncthreads();
-          if (tid == 0) {
-            double v = red_v[0];
-            int ix = red_i[0];
-            for (int w = 1; w < 16; ++w)
-              if (red_v[w] > v || (red_v[w] == v && red_i[w] >= 0 && (ix < 0 || red_i[w] < ix))) { v = red_v[w]; ix = red_i[w]; }
-            s_p = ix;
-            s_piv = v;
-          }
-          __syncthreads();
-          const int pv = s_p;
-          const double piv = s_piv;
-          if (pv < 0 || !(piv > tol)) { finished = true; break; }   // numerical rank reached (uniform)
+          int best_w = 0;
+          key = red_k[0];
+#pragma unroll
+          for (int w = 1; w < 16; ++w)
+            if (red_k[w] > key) { key = red_k[w]; best_w = w; }
+          const int pv = static_cast<int>(key & 0x7ffull);
+          const double piv = key ? red_d[best_w] : NEG;
+          if (!(piv > tol)) { finished = true; break; }   // numerical rank reached (uniform)
           const double root = sqrt(piv);
           const double rs = 1.0 / root;
           for (int i = tid; i < d; i += blockDim.x) {
-            double v = __ldcg(Am + static_cast<long long>(pv) * d + i);
-            for (int k = 0; k < jj; ++k) v = fma(-Lp[k * d + i], Lp[k * d + pv], v);
-            const double di = dg[i];
+            const double a = __ldcg(Am + static_cast<long long>(pv) * d + i);   // in flight during the dot product
+            double s0 = 0.0, s1 = 0.0;
+            int k = 0;
+            for (; k + 1 < jj; k += 2) {
+              s0 = fma(Lp[k * d + i], Lp[k * d + pv], s0);
+              s1 = fma(Lp[(k + 1) * d + i], Lp[(k + 1) * d + pv], s1);
+            }
+            if (k < jj) s0 = fma(Lp[k * d + i], Lp[k * d + pv], s0);
+            const double v = a - (s0 + s1);
+            const double di = dg[i];                    // own entries only: no other thread reads dg[i]
             double col = di == NEG ? 0.0 : v * rs;      // rows already used: exactly zero
             if (i == pv) { col = root; dg[i] = NEG; }
             else if (di != NEG) dg[i] = di - col * col;
             Lp[jj * d + i] = col;
           }
-          __syncthreads();
           ++npan;
         }
+        __syncthreads();
         for (int e = tid; e < npan * d; e += blockDim.x)
           Ltm[static_cast<long long>(j0) * d + e] = Lp[e];
       }
