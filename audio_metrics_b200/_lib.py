@@ -62,6 +62,7 @@ SIGNATURES = {
     "amb_host_kd": (_i, [_i, _vp, _ll, _vp, _ll, _i, _i, _vp, _i, _i, _dbl, _dbl, _i, _vp, _vp]),
     "amb_host_knn_radii": (_i, [_i, _vp, _i, _ll, _i, _i, _vp]),
     "amb_host_prdc": (_i, [_i, _vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
+    "amb_host_evaluate": (_i, [_vp, _i, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "amb_debug_dot_matrix": (_i, [_i, _vp, _vp, _ll, _vp, _ll, _i, _vp, _ll, C.c_uint, C.c_uint]),
 }
 

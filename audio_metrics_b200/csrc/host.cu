@@ -3,6 +3,11 @@
 // device-pointer entry points as everyone else on a private stream, and
 // synchronise before returning.  This is the surface a numpy / ctypes binding of
 // the reference's metric functions calls directly.
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "internal.cuh"
@@ -58,6 +63,190 @@ struct HostCall {
 };
 
 static size_t esize(int dtype) { return dtype == AMB_F64 ? 8 : 4; }
+
+// Reusable barrier for the worker threads of amb_host_evaluate (one thread per device).
+class ThreadBarrier {
+ public:
+  explicit ThreadBarrier(int n) : n_(n) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu_);
+    const int gen = gen_;
+    if (++count_ == n_) {
+      count_ = 0;
+      ++gen_;
+      cv_.notify_all();
+    } else {
+      cv_.wait(lk, [&] { return gen != gen_; });
+    }
+  }
+
+ private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  int n_, count_ = 0, gen_ = 0;
+};
+
+// 256-aligned even split of n rows over `world` workers (the CTA-pair engine takes row tiles in pairs)
+static void even_rows(long long n, int world, int rank, long long* row0, long long* nrows) {
+  long long chunk = (n + world - 1) / world;
+  chunk = (chunk + 255) / 256 * 256;
+  long long a = chunk * rank, b = a + chunk;
+  if (a > n) a = n;
+  if (b > n) b = n;
+  *row0 = a;
+  *nrows = b - a;
+}
+
+struct EvalShared {
+  // inputs
+  const void* ref; const void* cand; long long n, m; int d, dtype, k;
+  const int32_t* kd_idx; int S, msub; int want_fad; int n_dev;
+  // exchanged between the devices through host memory
+  std::vector<float> r_ref, r_cand;
+  std::vector<long long> totals;      // [n_dev][4]
+  double fad = 0, kd[2] = {0, 0};
+  std::vector<int> rc;
+  std::vector<std::string> err;
+};
+
+// One device's share of amb_host_evaluate.
+static void eval_worker(EvalShared* sh, ThreadBarrier* bar, int rank, int dev) {
+  const long long n = sh->n, m = sh->m;
+  const int d = sh->d, dtype = sh->dtype, k = sh->k;
+  int& rc_out = sh->rc[rank];
+  auto fail = [&](int rc) {
+    rc_out = rc;
+    sh->err[rank] = amb_last_error();
+  };
+  bool alive = true;
+  {
+    HostCall h(dev);
+    const bool want_prdc = k > 0;
+    const bool first = rank == 0;
+    void* dR = nullptr; void* dC = nullptr; void* pR = nullptr; void* pC = nullptr;
+    float* rR = nullptr; float* rC = nullptr;
+    long long r0 = 0, rn = 0, c0 = 0, cn = 0;
+    size_t wsb = 0;
+    void* ws = nullptr;
+    if (want_prdc || first) {
+      dR = h.upload_raw(sh->ref, static_cast<size_t>(n) * d * esize(dtype));
+      dC = h.upload_raw(sh->cand, static_cast<size_t>(m) * d * esize(dtype));
+    }
+    // ---- N-independent metrics on the first device, queued behind its uploads
+    double* fad_dev = nullptr; double* kd_dev = nullptr;
+    if (first && sh->want_fad && !h.rc) {
+      const size_t dd = static_cast<size_t>(d) * d;
+      double* mom = h.alloc<double>(2 * (d + dd));
+      double* st = h.alloc<double>(2 * (d + dd));
+      fad_dev = h.alloc<double>(1);
+      const size_t cw = amb_cov_ws_bytes(n > m ? n : m, d), fw = amb_frechet_ws_bytes(1, d);
+      void* w = h.alloc<uint8_t>(cw > fw ? cw : fw);
+      if (!h.rc) {
+        h.zero(mom, 2 * (d + dd) * 8);
+        double* mr = mom; double* mc = mom + d + dd;
+        h.run(amb_cov_accumulate(dev, h.st, dR, dtype, n, d, d, mr, mr + d, w, cw));
+        h.run(amb_cov_accumulate(dev, h.st, dC, dtype, m, d, d, mc, mc + d, w, cw));
+        double* sr = st; double* sc = st + d + dd;
+        h.run(amb_cov_finalize(dev, h.st, n, d, mr, mr + d, sr, sr + d));
+        h.run(amb_cov_finalize(dev, h.st, m, d, mc, mc + d, sc, sc + d));
+        h.run(amb_frechet(dev, h.st, 1, d, sc, sc + d, sr, sr + d, fad_dev, w, fw));   // (cand, ref): audio_metrics.py:257
+      }
+    }
+    if (first && sh->kd_idx && !h.rc) {
+      int32_t* didx = h.upload(sh->kd_idx, static_cast<size_t>(sh->S) * 2 * sh->msub);
+      kd_dev = h.alloc<double>(2);
+      const size_t kw = amb_kd_ws_bytes(sh->S, sh->msub, d);
+      void* w = h.alloc<uint8_t>(kw);
+      if (!h.rc)
+        h.run(amb_kd_subsets(dev, h.st, dC, m, d, dR, n, d, d, dtype, didx, sh->S, sh->msub, AMB_KERNEL_POLY, 1.0 / d, 1.0, 3,
+                             1.0, AMB_MMD_UNBIASED, nullptr, kd_dev, w, kw));                // features_1 = candidate
+    }
+    // ---- radii of this device's row shards
+    if (want_prdc && !h.rc) {
+      even_rows(n, sh->n_dev, rank, &r0, &rn);
+      even_rows(m, sh->n_dev, rank, &c0, &cn);
+      pR = h.alloc<uint8_t>(amb_packed_bytes(n, d));
+      pC = h.alloc<uint8_t>(amb_packed_bytes(m, d));
+      rR = h.alloc<float>(n);
+      rC = h.alloc<float>(m);
+      wsb = amb_knn_ws_bytes(rn, n, d, k);
+      const size_t w2 = amb_knn_ws_bytes(cn, m, d, k), w3 = amb_prdc_ws_bytes(n, m);
+      wsb = wsb > w2 ? wsb : w2;
+      wsb = wsb > w3 ? wsb : w3;
+      ws = h.alloc<uint8_t>(wsb);
+      if (!h.rc) {
+        h.run(amb_pack(dev, h.st, dR, dtype, n, d, d, pR));
+        h.run(amb_pack(dev, h.st, dC, dtype, m, d, d, pC));
+        h.run(amb_knn_radii(dev, h.st, dR, dtype, d, pR, n, d, r0, rn, k, rR + r0, nullptr, ws, wsb));
+        h.run(amb_knn_radii(dev, h.st, dC, dtype, d, pC, m, d, c0, cn, k, rC + c0, nullptr, ws, wsb));
+        h.download(sh->r_ref.data() + r0, rR + r0, static_cast<size_t>(rn));
+        h.download(sh->r_cand.data() + c0, rC + c0, static_cast<size_t>(cn));
+      }
+    }
+    if (fad_dev) h.download(&sh->fad, fad_dev, 1);
+    if (kd_dev) h.download(sh->kd, kd_dev, 2);
+    h.finish();
+    if (h.rc) { fail(h.rc); alive = false; }
+    bar->wait();                                    // every device's radii slices are in host memory
+    for (int q = 0; q < sh->n_dev; ++q) alive = alive && sh->rc[q] == AMB_OK;
+    // ---- counts of this device's reference rows against all candidates
+    if (alive && want_prdc) {
+      int32_t* col = h.alloc<int32_t>(m);
+      uint8_t* rec = h.alloc<uint8_t>(rn ? rn : 1);
+      uint8_t* cov = h.alloc<uint8_t>(rn ? rn : 1);
+      long long* totals = h.alloc<long long>(8);
+      if (!h.rc) {
+        h.rc = check_cuda(cudaMemcpyAsync(rR, sh->r_ref.data(), static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h.st), "H2D");
+        if (!h.rc) h.rc = check_cuda(cudaMemcpyAsync(rC, sh->r_cand.data(), static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, h.st), "H2D");
+      }
+      long long t[8] = {0};
+      void* big = nullptr;
+      // the overflow ladder of amb200.h: default list -> list of the reported size -> exhaustive kernel
+      for (int attempt = 0; attempt < 3 && !h.rc; ++attempt) {
+        h.zero(col, static_cast<size_t>(m) * 4);
+        h.zero(totals, 64);
+        if (attempt == 0)
+          h.run(amb_prdc_counts(dev, h.st, dR, d, pR, n, rR, dC, d, pC, m, rC, d, dtype, r0, rn, col, rec, cov, totals + 4, ws, wsb));
+        else if (attempt == 1 && big)
+          h.run(amb_prdc_counts(dev, h.st, dR, d, pR, n, rR, dC, d, pC, m, rC, d, dtype, r0, rn, col, rec, cov, totals + 4, big,
+                                amb_prdc_ws_bytes_cap(n, m, t[4])));
+        else
+          h.run(amb_prdc_counts_exact(dev, h.st, dR, d, n, rR, dC, d, m, rC, d, dtype, r0, rn, col, rec, cov));
+        // per-device partial numerators: sum of counts and row flags (the "columns with a hit" count
+        // needs the column vector summed over devices first, done on the host below)
+        h.run(amb_prdc_reduce(dev, h.st, nullptr, 0, rec, cov, rn, totals));
+        h.download(t, totals, 8);
+        h.finish();
+        if (h.rc) break;
+        const long long cap = attempt == 0 ? amb_prdc_ws_list_cap(n, m, wsb) : t[4];
+        if (attempt == 2 || t[4] <= cap) break;
+        if (attempt == 0) {
+          size_t free_b = 0, total_b = 0;
+          const size_t bb = amb_prdc_ws_bytes_cap(n, m, t[4]);
+          if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bb < free_b / 2 && cudaMalloc(&big, bb) == cudaSuccess)
+            h.bufs.push_back(big);
+          else
+            big = nullptr;
+          (void)cudaGetLastError();
+        }
+      }
+      if (!h.rc) {   // column counts of this shard -> host, summed by the caller
+        std::vector<int32_t> hc(static_cast<size_t>(m));
+        h.download(hc.data(), col, static_cast<size_t>(m));
+        h.finish();
+        if (!h.rc) {
+          static std::mutex mu;
+          std::lock_guard<std::mutex> lk(mu);
+          int32_t* acc = reinterpret_cast<int32_t*>(sh->totals.data() + 4 * sh->n_dev);   // [m] int32 after the per-device slots
+          for (long long j = 0; j < m; ++j) acc[j] += hc[j];
+          sh->totals[4 * rank + 2] = t[2];
+          sh->totals[4 * rank + 3] = t[3];
+        }
+      }
+      if (h.rc) fail(h.rc);
+    }
+  }
+}
 
 }  // namespace amb
 
@@ -203,6 +392,49 @@ int amb_host_prdc(int dev, const void* ref, long long n, const void* cand, long 
   out[1] = static_cast<double>(t[2]) / static_cast<double>(n);                         // recall     prdc.py:40-42
   out[2] = (1.0 / static_cast<double>(k)) * (static_cast<double>(t[1]) / static_cast<double>(m));  // density prdc.py:44-46
   out[3] = static_cast<double>(t[3]) / static_cast<double>(n);                         // coverage   prdc.py:48
+  return AMB_OK;
+}
+
+int amb_host_evaluate(const int* devs, int n_dev, const void* ref, long long n, const void* cand, long long m, int d,
+                      int dtype, int k, const int32_t* kd_idx, int S, int msub, int want_fad, double* out) {
+  if (!devs || n_dev < 1 || n_dev > 64 || !ref || !cand || !out || n <= 0 || m <= 0 || d <= 0 ||
+      (dtype != AMB_F32 && dtype != AMB_F64) || k < 0 || (kd_idx && (S <= 0 || msub <= 0)))
+    return set_error(AMB_ERR_ARG, "amb_host_evaluate: bad argument");
+  if (k > 0 && (k + 1 > n || k + 1 > m))
+    return set_error(AMB_ERR_ARG, "amb_host_evaluate: k=%d needs at least k+1 rows in both sets", k);
+  EvalShared sh;
+  sh.ref = ref; sh.cand = cand; sh.n = n; sh.m = m; sh.d = d; sh.dtype = dtype; sh.k = k;
+  sh.kd_idx = kd_idx; sh.S = S; sh.msub = msub; sh.want_fad = want_fad; sh.n_dev = n_dev;
+  if (k > 0) {
+    sh.r_ref.resize(static_cast<size_t>(n));
+    sh.r_cand.resize(static_cast<size_t>(m));
+  }
+  // [n_dev][4] per-device totals, followed by the summed per-candidate counts ([m] int32)
+  sh.totals.assign(static_cast<size_t>(4 * n_dev) + static_cast<size_t>((m + 1) / 2), 0);
+  sh.rc.assign(n_dev, AMB_OK);
+  sh.err.assign(n_dev, std::string());
+  const int workers = k > 0 ? n_dev : 1;          // without PRDC everything is N-independent: one device
+  sh.n_dev = workers;
+  ThreadBarrier bar(workers);
+  std::vector<std::thread> th;
+  for (int r = 0; r < workers; ++r) th.emplace_back(eval_worker, &sh, &bar, r, devs[r]);
+  for (auto& t : th) t.join();
+  for (int r = 0; r < workers; ++r)
+    if (sh.rc[r] != AMB_OK) return set_error(sh.rc[r], "amb_host_evaluate (device %d): %s", devs[r], sh.err[r].c_str());
+  const double nan = __builtin_nan("");
+  for (int i = 0; i < 7; ++i) out[i] = nan;
+  if (want_fad) out[0] = sh.fad;
+  if (kd_idx) { out[1] = sh.kd[0]; out[2] = sh.kd[1]; }
+  if (k > 0) {
+    const int32_t* col = reinterpret_cast<const int32_t*>(sh.totals.data() + 4 * workers);
+    long long hits = 0, total = 0, recalled = 0, covered = 0;
+    for (long long j = 0; j < m; ++j) { hits += col[j] > 0; total += col[j]; }
+    for (int r = 0; r < workers; ++r) { recalled += sh.totals[4 * r + 2]; covered += sh.totals[4 * r + 3]; }
+    out[3] = static_cast<double>(hits) / static_cast<double>(m);                                        // prdc.py:36-38
+    out[4] = static_cast<double>(recalled) / static_cast<double>(n);                                    // prdc.py:40-42
+    out[5] = (1.0 / static_cast<double>(k)) * (static_cast<double>(total) / static_cast<double>(m));    // prdc.py:44-46
+    out[6] = static_cast<double>(covered) / static_cast<double>(n);                                     // prdc.py:48
+  }
   return AMB_OK;
 }
 

@@ -5,11 +5,15 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one full pass of the hot path over one (reference, candidate) pair of
-synthetic CLAP-512 embedding sets: statistics + FAD, KD (100 x 1000 subsets) and
-PRDC (k = 5) at N = M = 200k, d = 512 — the configuration BASELINE.json quotes its
-metric on; it fits one B200 (0.4 GB per set).  With N > 1 ranks the rows are
-sharded (fixed total work: strong scaling) and the timed step includes the
-NCCL exchanges.  Prints ONE JSON line on rank 0.
+synthetic CLAP-512 embedding sets through the public API — AudioMetricsData.add of
+both sets, then the fused evaluation AudioMetrics.evaluate runs: statistics + FAD,
+KD (100 x 1000 subsets) and PRDC (k = 5) — at N = M = 200k, d = 512, the
+configuration BASELINE.json quotes its metric on; it fits one B200 (0.4 GB per
+set).  With N > 1 ranks the rows are sharded (fixed total work: strong scaling)
+and the timed step includes the NCCL exchanges.  Prints ONE JSON line on rank 0:
+`value` with the inputs resident in HBM, `e2e` with pinned host inputs (H2D inside
+the timed region), `e2e_c_abi` through the host-buffer C entry point, `parity`
+against the committed expectation, `phase_trace_ms` per phase of one step.
 """
 from __future__ import annotations
 
@@ -356,30 +360,26 @@ def run_b200_arm(args):
         idx = np.array(kd_subset_indices(N_CAND, N_REF, KD_SUBSET_SIZE, KD_SUBSETS, 1234), copy=True)
         d = DIM
 
+        devs = (C.c_int * 1)(local)
+
         def cabi_step():
-            mean_r, cov_r = np.empty(d), np.empty((d, d))
-            mean_c, cov_c = np.empty(d), np.empty((d, d))
-            _lib.check(L.amb_host_stats(local, rh.ctypes.data, 0, N_REF, d, mean_r.ctypes.data, cov_r.ctypes.data))
-            _lib.check(L.amb_host_stats(local, ch.ctypes.data, 0, N_CAND, d, mean_c.ctypes.data, cov_c.ctypes.data))
-            fad = C.c_double()
-            _lib.check(L.amb_host_frechet(local, d, mean_c.ctypes.data, cov_c.ctypes.data, mean_r.ctypes.data,
-                                          cov_r.ctypes.data, C.byref(fad)))
-            kd = (C.c_double * 2)()
-            _lib.check(L.amb_host_kd(local, ch.ctypes.data, N_CAND, rh.ctypes.data, N_REF, d, 0, idx.ctypes.data,
-                                     KD_SUBSETS, KD_SUBSET_SIZE, 1.0 / d, 1.0, 3, None, kd))
-            out = (C.c_double * 4)()
-            _lib.check(L.amb_host_prdc(local, rh.ctypes.data, N_REF, ch.ctypes.data, N_CAND, d, 0, K_NN, out))
-            return {"fad": fad.value, "kernel_distance_mean": kd[0], "kernel_distance_std": kd[1],
-                    "precision": out[0], "recall": out[1], "density": out[2], "coverage": out[3]}
+            out = (C.c_double * 7)()
+            _lib.check(L.amb_host_evaluate(devs, 1, rh.ctypes.data, N_REF, ch.ctypes.data, N_CAND, d, 0, K_NN,
+                                           idx.ctypes.data, KD_SUBSETS, KD_SUBSET_SIZE, 1, out))
+            return dict(zip(("fad", "kernel_distance_mean", "kernel_distance_std", "precision", "recall", "density",
+                             "coverage"), out))
 
         cabi_step()
         t0 = time.perf_counter()
         res_cabi = cabi_step()
         dt = time.perf_counter() - t0
-        e2e_cabi = {"value": pairs / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": 3 * h2d,
-                    "clock": "host wall clock around five synchronous amb_host_* calls (each stages its own "
-                             "inputs from pageable host memory: 3 x the input bytes cross PCIe)",
-                    "result": res_cabi}
+        e2e_cabi = {"value": pairs / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": h2d,
+                    "clock": "host wall clock around ONE amb_host_evaluate call on numpy arrays in pageable host "
+                             "memory (device allocation, upload, every kernel, read-back and free inside)",
+                    "result": res_cabi,
+                    "agrees_with_python_path": all(
+                        res_cabi[k] == result[k] if k in ("precision", "recall", "density", "coverage")
+                        else abs(res_cabi[k] - result[k]) <= 1e-9 * abs(result[k]) for k in result)}
 
     # ---- where the time of one step goes on this rank and on the last one (CUDA events between phases)
     from audio_metrics_b200 import dist as amb_dist
@@ -412,7 +412,7 @@ def run_b200_arm(args):
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops"], "traffic": load_traffic(),
-        "kernel": "pair_engine2_kernel<TopkEpi|CountEpi> (tcgen05 kind::f16 cta_group::2, one MMA per product, A panels resident in smem) + pair_engine_kernel<KdEpi> (3-MMA split)",
+        "kernel": "pair_engine2_kernel<TopkEpi|CountEpi> (tcgen05 kind::f16 cta_group::2, one MMA per product, A panels resident in smem) + pair_engine_kernel<KdEpi> (3-MMA split); with N > 1 ranks: rank 0's launches (the rank that also computes the Frechet distance sweeps 1 - N F / (W + F) of an even share)",
         "launches_timed": int(eng_launches), "avg_launch_ms": eng_ms / eng_launches if eng_launches else None,
         "kernel_share_of_step": eng_ms / (ms_step * args.steps) if ms_step > 0 else None,
         "executed_tflops": executed, "executed_frac": executed / peaks["tflops"], "peak_source": peaks["source"],

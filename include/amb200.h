@@ -241,6 +241,22 @@ int amb_host_knn_radii(int dev, const void* X, int dtype, long long n, int d, in
 int amb_host_prdc(int dev, const void* ref, long long n, const void* cand, long long m, int d,
                   int dtype, int k, double* out);
 
+/* Everything AudioMetrics.evaluate computes after embedding (audio_metrics.py:254-264) in ONE call on
+ * host arrays, sharded over the n_dev devices of devs[] inside this process (one worker thread per
+ * device — the reference's multi-GPU mechanism is threads in one process too,
+ * util/gpu_parallel.py:20-76): every device uploads the rows once, takes a 256-aligned row shard of
+ * both all-pairs sweeps against all columns, and exchanges radii slices and per-candidate counts
+ * through host memory; statistics, the Frechet distance and the kernel distance run on devs[0]
+ * behind its uploads.  No NCCL, no process group.
+ *   want_fad != 0           out[0] = Frechet distance of (candidate, reference)
+ *   kd_idx != NULL          out[1], out[2] = kernel_distance_mean / _std; kd_idx [S, 2, msub] int32 as
+ *                           amb_kd_subsets (drawn for features_1 = candidate, features_2 = reference)
+ *   k > 0                   out[3..6] = precision, recall, density, coverage (prdc.py:50)
+ * Entries that were not asked for are NaN. */
+int amb_host_evaluate(const int* devs, int n_dev, const void* ref, long long n, const void* cand,
+                      long long m, int d, int dtype, int k, const int32_t* kd_idx, int S, int msub,
+                      int want_fad, double* out);
+
 /* ------------------------------------------------------------- debug / validation
  * Full dot-product matrix through the tensor-core engine (small sizes only):
  * C[i*ldc + j] = <A_i, B_j> from packed operands; with ldc == 0 only the row

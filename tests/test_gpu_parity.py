@@ -272,3 +272,32 @@ def test_host_buffer_entry_points(cuda_device):
     exact = np.partition(cdist_exact(ref, ref), 5, axis=-1)[:, 5]
     np.testing.assert_allclose(radii, exact.astype(np.float32), rtol=2e-7)
     assert L.amb_host_prdc(0, ref.ctypes.data, 700, cand.ctypes.data, 900, 128, 0, 0, out) == _lib.AMB_ERR_ARG
+
+
+def test_host_evaluate_one_call(cuda_device):
+    """amb_host_evaluate: FAD + KD + PRDC of two numpy arrays in one C call (and, with two GPUs, sharded
+    over both inside the process) equals the Python path on the same inputs."""
+    import ctypes as C
+    from audio_metrics_b200.dist import evaluate_containers
+    L = _lib.lib()
+    ref, cand = make_sets_numpy(3100, 2700, 96, seed=23)
+    idx = oracle.draw_subset_indices(2700, 3100, 500, 30)
+    want = evaluate_containers(_amd(ref), _amd(cand), ("fad", "kd", "prdc"), nearest_k=5, kd_subsets=30, kd_subset_size=500)
+    keys = ("fad", "kernel_distance_mean", "kernel_distance_std", "precision", "recall", "density", "coverage")
+    for n_dev in range(1, min(2, torch.cuda.device_count()) + 1):
+        devs = (C.c_int * n_dev)(*range(n_dev))
+        out = (C.c_double * 7)()
+        _lib.check(L.amb_host_evaluate(devs, n_dev, ref.ctypes.data, 3100, cand.ctypes.data, 2700, 96, 0, 5,
+                                       idx.ctypes.data, 30, 500, 1, out))
+        got = dict(zip(keys, out))
+        assert got["fad"] == pytest.approx(want["fad"], rel=1e-12)
+        for key in keys[1:3]:
+            assert got[key] == pytest.approx(want[key], rel=1e-12), key
+        for key in keys[3:]:
+            assert got[key] == want[key], key
+    # subsets of the metrics: the others come back as NaN
+    out = (C.c_double * 7)()
+    devs = (C.c_int * 1)(0)
+    _lib.check(L.amb_host_evaluate(devs, 1, ref.ctypes.data, 3100, cand.ctypes.data, 2700, 96, 0, 0, None, 0, 0, 1, out))
+    assert out[0] == pytest.approx(want["fad"], rel=1e-12) and all(np.isnan(v) for v in list(out)[1:])
+    assert L.amb_host_evaluate(devs, 1, ref.ctypes.data, 3, cand.ctypes.data, 2700, 96, 0, 5, None, 0, 0, 1, out) == _lib.AMB_ERR_ARG
