@@ -50,6 +50,31 @@ def _world(group):
     return 1, 0
 
 
+def _allgather_rows_start(x: torch.Tensor, counts, group):
+    """Asynchronous form of _allgather_rows: issues the collective now (it runs on NCCL's own stream,
+    beside whatever is queued on the current stream afterwards) and returns a function that makes the
+    current stream wait for it and hands out the gathered rows."""
+    world, _ = _world(group)
+    if world == 1:
+        return lambda: x
+    maxc = max(max(counts), 1)
+    if x.shape[0] == maxc and x.is_contiguous():
+        pad = x
+    else:
+        pad = torch.zeros((maxc,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        pad[: x.shape[0]] = x
+    out = torch.empty((world * maxc,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    work = dist.all_gather_into_tensor(out, pad, group=group, async_op=True)
+
+    def finish(pad=pad):
+        work.wait()
+        if all(c == maxc for c in counts[:-1]):
+            return out[: sum(counts)]
+        return torch.cat([out[r * maxc: r * maxc + counts[r]] for r in range(world)])
+
+    return finish
+
+
 def _allgather_rows(x: torch.Tensor, counts, group):
     """All ranks' row blocks, concatenated in rank order.  ``counts[r]`` = rows rank r contributes
     (any sizes: who holds which rows is the caller's business, e.g. wherever the embedder left them).
@@ -377,16 +402,20 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
     with_fad = bool(want_fad or extra_fad)
     weights = work_weights(world, n_ref, n_cand, d, with_fad) if ref is not None else [1.0] * world
 
-    def full(s):
-        """Container over ALL rows of the set — gathered once per set (cached with the set)."""
+    def full(s, prefetch=False):
+        """Container over ALL rows of the set — gathered once per set (cached with the set).
+        ``prefetch``: only start the allgather (it then overlaps the work queued next: the candidate's
+        rows travel while the reference sweep runs); the next call completes it."""
         if world == 1 and isinstance(s, _Held):
             return s.c                       # the container itself (never cached inside itself: no cycles)
         key = ("full", world, id(group))
         hit = s.cache.get(key)
         if hit is None:
             assert sum(s.counts) == s.n_total, "row counts of the ranks do not add up to the set size"
-            hit = s.cache[key] = s.full_container(_allgather_rows(s.rows(), s.counts, group))
-        return hit
+            hit = s.cache[key] = ("pending", _allgather_rows_start(s.rows(), s.counts, group))
+        if isinstance(hit, tuple) and not prefetch:
+            hit = s.cache[key] = s.full_container(hit[1]())
+        return None if isinstance(hit, tuple) else hit
 
     def radii(s, n):
         c = full(s)
@@ -467,6 +496,8 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
     if want_prdc and not done_ref_sweep:
         full(ref)
         _mark("allgather reference", tdev)
+        if world > 1:
+            full(cand, prefetch=True)        # the candidate's rows travel while the reference sweep runs
         full(ref).packed() if hasattr(full(ref), "packed") else None
         _mark("pack reference", tdev)
         r_ref = radii(ref, n_ref)
