@@ -646,6 +646,22 @@ def evaluate_containers(ref, cand, metrics=("fad", "kd", "prdc"), nearest_k=5, g
                   kd_seed=kd_seed)
 
 
+def global_stats(c, group=None):
+    """(n, mean, cov) of a set whose rows are spread over the ranks, from each rank's container: one
+    small exchange of row counts and one allreduce of the raw moments.  With no process group this
+    is the container's own statistics."""
+    world, _ = _world(group)
+    if world == 1:
+        return c.n, c.mean, c.cov
+    ops = default_ops(c.device)
+    meta = _gather_meta([c.n or 0, _width(c) or 0], ops.device, group)
+    n, d = sum(m[0] for m in meta), max(m[1] for m in meta)
+    mom = c.local_moments() if c.n else torch.zeros(d + d * d, dtype=torch.float64, device=ops.device)
+    _allreduce(mom, group)
+    mean, cov = ops.stats_from_moments(mom, n, d)
+    return n, mean, cov
+
+
 # ------------------------------------------------------------------ one process, several GPUs
 def _replica(c, dev):
     """A container with the same rows on another device of this process (peer copy over NVLink),

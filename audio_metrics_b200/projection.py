@@ -50,9 +50,14 @@ class IncrementalPCA:
         else:
             c = AudioMetricsData(store_embeddings=False, device=self.device)
             c.add(x)
-        d = c.mean.shape[0]
-        cov = c.cov if tuple(c.cov.shape) == (d, d) else torch.zeros((d, d), dtype=torch.float64, device=self.device)
-        return c.n, c.mean, cov
+        # under torch.distributed the containers hold each rank's rows: fit on the statistics of the whole set
+        from .dist import global_stats
+
+        n, mean, cov = global_stats(c)
+        d = mean.shape[0]
+        if tuple(cov.shape) != (d, d):
+            cov = torch.zeros((d, d), dtype=torch.float64, device=self.device)
+        return n, mean, cov
 
     # ---------------------------------------------------------------------- fit
     def partial_fit(self, x, y=None, check_input=True):
