@@ -173,6 +173,8 @@ class AudioMetrics:
         # reference's one call and one host synchronisation per metric (:254-272); under
         # torch.distributed the containers hold this rank's rows and the step is row-sharded.
         fused = tuple(m for m in ("fad", "kd", "prdc") if m in self.metrics) if self.stems_mode else ()
+        if not fused and apa_sets is None:
+            return {}
         if len(self.devices) > 1 and not (torch.distributed.is_available() and torch.distributed.is_initialized()):
             res = evaluate_devices(stem_ref if fused else None, stem_cand if fused else None, self.devices, fused,
                                    nearest_k=None, apa=apa_sets)

@@ -547,7 +547,7 @@ polar_init_kernel(const double* __restrict__ Mt, int d, int dp, double* __restri
 // fed across shared-memory and barrier latencies.  A thread's columns are {2 tx, 2 tx + 1, 32 + 2 tx,
 // 33 + 2 tx}: its two 16-byte reads of a B row are conflict free.  At d = 512: 128 CTAs, one wave.
 template <int MODE>
-__global__ void __launch_bounds__(kPgThreads)
+__global__ void __launch_bounds__(kPgThreads, 1)
 polar_gemm_kernel(const double* __restrict__ X, const double* __restrict__ Q, double* __restrict__ C, int dp, int step) {
   extern __shared__ __align__(16) double pg_smem[];
   const long long mo = static_cast<long long>(blockIdx.z) * dp * dp;
@@ -589,25 +589,33 @@ polar_gemm_kernel(const double* __restrict__ X, const double* __restrict__ Q, do
     cp_async_commit();
     const double* st = pg_smem + static_cast<size_t>(kb % kPgStages) * kPgStageDoubles;
     const double* bs = st + kPgATile;
+    // this group's eight k steps of the block, four at a time: all operand loads of a half are issued
+    // before its 64 FMAs, so the shared-memory latency is paid once per half instead of once per step
+    // (with two warps per scheduler the loads of one step could not hide behind the FMAs of another)
 #pragma unroll
-    for (int q = 0; q < kPgK / 2; ++q) {
-      const int kk = 2 * q + grp;
-      double a[4];
-      if (MODE == 2) {
+    for (int hq = 0; hq < 2; ++hq) {
+      double a[4][4], b[4][4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) a[r] = st[(ty * 4 + r) * kPgA2Stride + kk];
-      } else {
-        const double2 a0 = *reinterpret_cast<const double2*>(st + kk * kPgAStride + ty * 4);
-        const double2 a1 = *reinterpret_cast<const double2*>(st + kk * kPgAStride + ty * 4 + 2);
-        a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y;
+      for (int q = 0; q < 4; ++q) {
+        const int kk = 2 * (4 * hq + q) + grp;
+        if (MODE == 2) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) a[q][r] = st[(ty * 4 + r) * kPgA2Stride + kk];
+        } else {
+          const double2 a0 = *reinterpret_cast<const double2*>(st + kk * kPgAStride + ty * 4);
+          const double2 a1 = *reinterpret_cast<const double2*>(st + kk * kPgAStride + ty * 4 + 2);
+          a[q][0] = a0.x; a[q][1] = a0.y; a[q][2] = a1.x; a[q][3] = a1.y;
+        }
+        const double2 b0 = *reinterpret_cast<const double2*>(bs + kk * kPgBStride + 2 * tx);
+        const double2 b1 = *reinterpret_cast<const double2*>(bs + kk * kPgBStride + 32 + 2 * tx);
+        b[q][0] = b0.x; b[q][1] = b0.y; b[q][2] = b1.x; b[q][3] = b1.y;
       }
-      const double2 b0 = *reinterpret_cast<const double2*>(bs + kk * kPgBStride + 2 * tx);
-      const double2 b1 = *reinterpret_cast<const double2*>(bs + kk * kPgBStride + 32 + 2 * tx);
-      const double b[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[q][r], b[q][c], acc[r][c]);
     }
   }
   cp_async_wait<0>();

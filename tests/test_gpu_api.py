@@ -74,6 +74,37 @@ def test_inputs_ndarray_generator_tensor(cuda_device):
     _check(am.evaluate(rng.random((40, n))), ["fad"])
 
 
+def test_apa_only_and_metric_subsets(cuda_device):
+    """metrics=["apa"] (no stem sets at all), single metrics, and the fused result against the
+    separate metric functions on the facade's own containers."""
+    from audio_metrics_b200 import apa, frechet_distance, kernel_distance, prdc
+    rng = np.random.default_rng(4)
+    n = 5 * 16000
+    ref, cand = rng.standard_normal((90, n, 2)), rng.standard_normal((80, n, 2))
+    am = AudioMetrics(embedder=RandomEmbedder(), mix_function=mix_func, metrics=["apa"])
+    am.add_reference(ref)
+    out = am.evaluate(cand)
+    _check(out, ["apa"])
+    assert am.stem_reference is None and 0.0 <= out["apa"] <= 1.0
+    for metrics, keys in ((["kd"], ["kernel_distance_mean", "kernel_distance_std"]),
+                          (["prdc"], ["precision", "recall", "density", "coverage"]), (["fad"], ["fad"])):
+        am = AudioMetrics(embedder=RandomEmbedder(), mix_function=mix_func, metrics=metrics)
+        am.add_reference(ref)
+        _check(am.evaluate(cand), keys)
+    # fused step == the reference's one-call-per-metric sequence (audio_metrics.py:254-272) on the same containers
+    am = AudioMetrics(embedder=RandomEmbedder(), mix_function=mix_func, metrics=["fad", "kd", "prdc", "apa"])
+    am.add_reference(ref)
+    got = am.evaluate(cand)
+    from audio_metrics_b200.pipeline import ItemCategory, embedding_pipeline
+    data = am._embed(cand, "candidate")
+    sc, ac = data[ItemCategory.stem], data[ItemCategory.aligned]
+    k = max(1, min(10, len(am.stem_reference), len(sc)))
+    want = dict(fad=frechet_distance(sc, am.stem_reference), **kernel_distance(sc, am.stem_reference),
+                **prdc(am.stem_reference, sc, k), apa=apa(ac, am.mix_reference, am.mix_anti_reference))
+    for key in want:
+        assert got[key] == pytest.approx(want[key], rel=1e-9, abs=1e-12), key
+
+
 def test_mono_input_with_apa_raises(cuda_device):
     am = _am()
     with pytest.raises(ValueError):
