@@ -16,6 +16,7 @@ constexpr float kInf = __builtin_huge_valf();
 struct DumpEpi {
   static constexpr int kColVecs = 1;
   static constexpr bool kScratch = false;
+  static constexpr bool kChunkMin = false;
   const float* inv_a;
   const float* inv_b;
   float* C;
@@ -31,6 +32,8 @@ struct DumpEpi {
     r.a_row = a_row;
     r.sum = 0.f;
   }
+  __device__ void tile_begin(Row&, const float (*)[kTileN]) const {}
+  template <bool>
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
                         long long b_row0, float*, float, float) const {
     if (r.a_row >= na) return;
@@ -59,6 +62,7 @@ struct DumpEpi {
 struct KdEpi {
   static constexpr int kColVecs = 1;
   static constexpr bool kScratch = false;
+  static constexpr bool kChunkMin = false;
   const float* inv_a;
   const float* inv_b;
   int kernel_type;
@@ -96,6 +100,8 @@ struct KdEpi {
       return exp(d2 * rbf_scale);
     }
   }
+  __device__ void tile_begin(Row&, const float (*)[kTileN]) const {}
+  template <bool>
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0,
                         int col0, long long b_row0, float*, float, float) const {
     if (!r.valid) return;
@@ -166,17 +172,6 @@ __host__ __device__ inline float band_key1(float nrm_x, float rho_x, float nrm_y
   return 2.0f * ((rho_x * ay + ax * rho_y_max) * 1.002f + kBandAcc1 * ax * ay) + kBandAbs * (nrm_x + nrm_y_max);
 }
 
-// Bound on the raw accumulator for "some column of this chunk has key  |y_j|^2 + sc acc_j < thr":
-// with |y_j|^2 >= cmin for the whole chunk and sc < 0 that needs  acc_j > (thr - cmin) / sc.  sc is a
-// power of two, so the quotient is exact; the bound is loosened by the fp32 rounding of the key
-// and of the difference.  NaN (thr = cmin = +inf) compares false, which is right: a chunk of padding
-// columns holds no candidates; thr = +inf (empty list) gives -inf, everything passes.
-__device__ __forceinline__ float raw_limit(float thr, float cmin, float sc) {
-  const float rs = __frcp_rn(sc);
-  const float lim = (thr - cmin) * rs;
-  return lim - ((fabsf(thr) + fabsf(cmin)) * fabsf(rs) + fabsf(lim)) * 2e-7f;
-}
-
 // -------------------------------------------------- per-row (k+1)-smallest lists
 // Ranking key for row i over columns j:  t_ij = |y_j|^2 - 2 <x_i, y_j>
 // (d_ij^2 = |x_i|^2 + t_ij).  Each thread keeps its row's K smallest approximate
@@ -188,6 +183,7 @@ template <int K>
 struct TopkEpi {
   static constexpr int kColVecs = 2;   // 0: inv_scale_b, 1: norm_b (+inf on padding)
   static constexpr bool kScratch = true;
+  static constexpr bool kChunkMin = true;   // the CTA-pair engine stages cmin_b next to the column vectors
   const float* inv_a;
   const float* inv_b;
   const float* norm_b;
@@ -202,7 +198,7 @@ struct TopkEpi {
   // lists together then take about as many insertions as one list over all columns would.
   // The refine kernel's certificate is unaffected: whatever a list rejected was >= some list's
   // K-th key at that time >= that list's final K-th key >= the K-th smallest of the union.
-  struct Row { float m2isr; float v[K]; int c[K]; float* mine; const volatile float* peer; };
+  struct Row { float m2isr, sc; float v[K]; int c[K]; float* mine; const volatile float* peer; };
   __device__ const float* colvec_ptr(int v) const { return v == 0 ? inv_b : norm_b; }
   __device__ const float* cmin_ptr() const { return cmin_b; }
   __device__ const float* cmax_ptr() const { return nullptr; }
@@ -214,76 +210,114 @@ struct TopkEpi {
     r.peer = xchg + (half ^ 1);
     *r.mine = kInf;
   }
+  // Sorted insert with no dependent chain: slot i of the new list is old slot i-1 if the key goes
+  // in front of it, the key itself if it lands here, old slot i otherwise — every slot from the OLD
+  // list and the key alone (ties: behind equal keys already present).  A key that is not below
+  // the last slot (or +inf from an idle lane) changes nothing.
+  __device__ __forceinline__ void insert(Row& r, float key, int col) const {
+    bool p[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) p[i] = key < r.v[i];
+#pragma unroll
+    for (int i = K - 1; i > 0; --i) {
+      r.v[i] = p[i - 1] ? r.v[i - 1] : (p[i] ? key : r.v[i]);
+      r.c[i] = p[i - 1] ? r.c[i - 1] : (p[i] ? col : r.c[i]);
+    }
+    r.v[0] = p[0] ? key : r.v[0];
+    r.c[0] = p[0] ? col : r.c[0];
+  }
+  // -2 / (scale_a scale_b) < 0: one value per column tile (a packed 256-row tile has one scale;
+  // powers of two, so the product is exact)
+  __device__ void tile_begin(Row& r, const float (*cv)[kTileN]) const { r.sc = cv[0][0] * r.m2isr; }
+  template <bool kStaged>
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
                         long long b_row0, float* scratch, float cmin, float) const {
-    const float sc = cv[0][c0] * r.m2isr;   // -2 / (scale_a scale_b): one per tile (powers of two, exact)
+    const float sc = r.sc;
     const float thr = fminf(r.v[K - 1], *r.peer);
-    // Cheapest test first, on the raw accumulators (kernels that stage the chunk minima): a candidate
-    // needs |y_j|^2 + sc acc_j < thr, and |y_j|^2 >= cmin for the whole chunk — see raw_limit().
-    if (cmin > -kInf) {
-      float mx = f32(acc[0]);
-#pragma unroll
-      for (int j = 1; j < 32; ++j) mx = fmaxf(mx, f32(acc[j]));
-      if (!__any_sync(0xffffffffu, mx > raw_limit(thr, cmin, sc))) return;
-    }
-    // branch-free scan next: most chunks hold nothing below the row's current K-th smallest key
-    float t[32];
-    float g[4];                              // minimum of each 8-column group
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      float ma = kInf, mb = kInf;
-#pragma unroll
-      for (int j = 8 * h; j < 8 * h + 8; j += 2) {
-        t[j + 0] = fmaf(f32(acc[j + 0]), sc, cv[1][c0 + j + 0]);
-        t[j + 1] = fmaf(f32(acc[j + 1]), sc, cv[1][c0 + j + 1]);
-        ma = fminf(ma, t[j + 0]);
-        mb = fminf(mb, t[j + 1]);
-      }
-      g[h] = fminf(ma, mb);
-    }
-    const float tmin = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
-    if (__any_sync(0xffffffffu, tmin < thr)) {
-      // some row of the warp takes new candidates.  Per 8-column group of the chunk that
-      // holds one: each thread builds the bit mask of its qualifying columns, parks the 8
-      // keys in its private shared-memory slots, and the warp loops while any lane still
-      // has a bit to consume (usually one trip): a lane picks its lowest set column, reloads
-      // that key by dynamic index and inserts it; the threshold tightens as it goes.
+    // Cheapest test first, on the raw accumulators, per 8-column group (kernels that stage the chunk
+    // minima): a candidate needs key_j = fma(acc_j, sc, |y_j|^2) < thr.  With m = max acc_j over the
+    // group and |y_j|^2 >= cmin over the chunk, acc_j sc + |y_j|^2 >= m sc + cmin as real numbers
+    // (sc < 0), and rounding is monotone, so key_j >= fma(m, sc, cmin): a group whose bound is not
+    // below thr holds nothing — an exact test, no slack.  Padding columns (|y|^2 = +inf) and an empty
+    // list (thr = +inf) come out right by themselves.
+    unsigned gm = 0xfu;                     // bit h: group h may hold a candidate of this row
+    if (kStaged) {
+      gm = 0;
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        if (!__any_sync(0xffffffffu, g[h] < thr)) continue;
-        unsigned mask = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          scratch[j] = t[8 * h + j];
-          mask |= (t[8 * h + j] < thr) ? (1u << j) : 0u;
-        }
-        while (__any_sync(0xffffffffu, mask != 0)) {
-          float key = kInf;
-          int col = -1;
-          if (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            key = scratch[j];
-            col = static_cast<int>(b_row0) + 8 * h + j;
-          }
-          if (key < r.v[K - 1]) {
-            r.v[K - 1] = key;
-            r.c[K - 1] = col;
-          }
-#pragma unroll
-          for (int i = K - 1; i > 0; --i) {
-            const bool sw = r.v[i] < r.v[i - 1];
-            const float va = r.v[i - 1], vb = r.v[i];
-            const int ca = r.c[i - 1], cb = r.c[i];
-            r.v[i - 1] = sw ? vb : va;
-            r.v[i] = sw ? va : vb;
-            r.c[i - 1] = sw ? cb : ca;
-            r.c[i] = sw ? ca : cb;
-          }
-        }
+        const float ma = fmaxf(fmaxf(f32(acc[8 * h + 0]), f32(acc[8 * h + 1])), fmaxf(f32(acc[8 * h + 2]), f32(acc[8 * h + 3])));
+        const float mb = fmaxf(fmaxf(f32(acc[8 * h + 4]), f32(acc[8 * h + 5])), fmaxf(f32(acc[8 * h + 6]), f32(acc[8 * h + 7])));
+        gm |= (fmaf(fmaxf(ma, mb), sc, cmin) < thr) ? (1u << h) : 0u;
       }
-      *r.mine = r.v[K - 1];
+      if (__builtin_expect(!__any_sync(0xffffffffu, gm != 0), 1)) return;
     }
+    // Some row of the warp may take new candidates.  Per group that can hold one: each thread
+    // evaluates its 8 keys, builds the bit mask of those below its threshold, parks the keys in its
+    // private shared-memory slots, and the warp loops while any lane still has a bit to consume
+    // (usually one trip): a lane picks its lowest set column, reloads that key by dynamic index and
+    // inserts it; the list's last key tightens as it goes.
+    // The groups are walked by a run-time loop (the warp-uniform switch moves the group's eight
+    // accumulators into fixed registers) so that the slow path exists once, not four times: the
+    // whole chunk loop then stays inside the instruction cache of the scheduler, and the far jumps
+    // around four unrolled copies cost more than the eight moves.
+    unsigned todo = __reduce_or_sync(0xffffffffu, gm);
+#pragma unroll 1
+    while (todo) {
+      const int h = __ffs(todo) - 1;
+      todo &= todo - 1;
+      float a[8];
+      switch (h) {
+        case 0:
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = f32(acc[j]);
+          break;
+        case 1:
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = f32(acc[8 + j]);
+          break;
+        case 2:
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = f32(acc[16 + j]);
+          break;
+        default:
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = f32(acc[24 + j]);
+          break;
+      }
+      // all loads before the stores: the scratch slots could alias the column vectors as far as the
+      // compiler knows, and a load held behind each store pays the shared-memory latency 8 times
+      const float4 na = *reinterpret_cast<const float4*>(&cv[1][c0 + 8 * h]);
+      const float4 nb = *reinterpret_cast<const float4*>(&cv[1][c0 + 8 * h + 4]);
+      float t[8];
+      t[0] = fmaf(a[0], sc, na.x);
+      t[1] = fmaf(a[1], sc, na.y);
+      t[2] = fmaf(a[2], sc, na.z);
+      t[3] = fmaf(a[3], sc, na.w);
+      t[4] = fmaf(a[4], sc, nb.x);
+      t[5] = fmaf(a[5], sc, nb.y);
+      t[6] = fmaf(a[6], sc, nb.z);
+      t[7] = fmaf(a[7], sc, nb.w);
+      unsigned mask = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mask |= (t[j] < thr) ? (1u << j) : 0u;
+      if (!__any_sync(0xffffffffu, mask != 0)) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) scratch[j] = t[j];   // stride-9 slots: scalar stores, conflict-free
+      const int col0 = static_cast<int>(b_row0) + 8 * h;
+#pragma unroll 1
+      do {
+        float key = kInf;
+        int col = -1;
+        if (mask) {
+          const int j = __ffs(mask) - 1;
+          mask &= mask - 1;
+          key = scratch[j];
+          col = col0 + j;
+        }
+        insert(r, key, col);
+      } while (__any_sync(0xffffffffu, mask != 0));
+    }
+    *r.mine = r.v[K - 1];
   }
   __device__ void row_end(Row& r, const ItemCoord& c, int, long long a_row, int, int, int half) const {
     const long long o = (static_cast<long long>(2 * c.split + half) * list_rows + (a_row - a_row_base)) * K;
@@ -304,6 +338,7 @@ struct PairEntry { uint32_t i; uint32_t j_kind; };   // j_kind: bit 31 = 1 -> in
 struct CountEpi {
   static constexpr int kColVecs = 4;   // 0: inv_scale_b, 1: norm_b, 2: B_hi, 3: B_lo
   static constexpr bool kScratch = false;
+  static constexpr bool kChunkMin = true;   // cmin_b and cmax_bhi are staged by the CTA-pair engine
   const float* inv_a;
   const float* norm_a;
   const float* a_lo;       // indexed by packed A row
@@ -322,7 +357,7 @@ struct CountEpi {
   PairEntry* list;         // uncertain pairs
   unsigned long long* list_count;
   unsigned long long list_cap;
-  struct Row { float m2isr, nx, Alo, Ahi; bool rec, cov; uint32_t i; };
+  struct Row { float m2isr, sc, nx, Alo, Ahi; bool rec, cov; uint32_t i; };
   __device__ const float* colvec_ptr(int v) const {
     return v == 0 ? inv_b : (v == 1 ? norm_b : (v == 2 ? b_hi : b_lo));
   }
@@ -341,20 +376,27 @@ struct CountEpi {
     const unsigned long long pos = atomicAdd(list_count, 1ull);
     if (pos < list_cap) list[pos] = PairEntry{i, j_kind};
   }
+  __device__ void tile_begin(Row& r, const float (*cv)[kTileN]) const { r.sc = cv[0][0] * r.m2isr; }
+  template <bool kStaged>
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
                         long long b_row0, float*, float cmin, float cmax) const {
     bool any_ref = false, any_cand = false;
-    const float sc = cv[0][c0] * r.m2isr;   // -2 / (scale_a scale_b): one per tile (powers of two, exact)
-    // Both tests first on the chunk as a whole, from the largest raw accumulator (raw_limit()):
+    const float sc = r.sc;                  // -2 / (scale_a scale_b): one per tile (powers of two, exact)
+    // Both tests first on the chunk as a whole, from the largest raw accumulator (exact bounds):
     //   in_ref  needs |y_j|^2 + sc acc_j < A_hi,   and |y_j|^2 >= cmin over the chunk;
     //   in_cand needs |x_i|^2 + sc acc_j < B_hi_j, and B_hi_j <= cmax over the chunk.
     // Kernels that do not stage the chunk arrays (cmin = -inf) test every column as before.
-    if (cmin > -kInf) {
-      float mx = f32(acc[0]);
+    if (kStaged) {
+      float m4[4];                           // four independent chains, then a tree
 #pragma unroll
-      for (int j = 1; j < 32; ++j) mx = fmaxf(mx, f32(acc[j]));
-      any_ref = mx > raw_limit(r.Ahi, cmin, sc);
-      any_cand = mx > raw_limit(cmax, r.nx, sc);
+      for (int h = 0; h < 4; ++h) {
+        m4[h] = f32(acc[8 * h]);
+#pragma unroll
+        for (int j = 1; j < 8; ++j) m4[h] = fmaxf(m4[h], f32(acc[8 * h + j]));
+      }
+      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      any_ref = fmaf(mx, sc, cmin) < r.Ahi;    // every t_j >= fma(mx, sc, cmin): see TopkEpi::chunk
+      any_cand = fmaf(mx, sc, r.nx) < cmax;    // every u_j >= fma(mx, sc, |x|^2), every B_hi_j <= cmax
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {

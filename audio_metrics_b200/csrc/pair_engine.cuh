@@ -159,12 +159,13 @@ __device__ __forceinline__ void epilogue_role(const EngineGeom& g, const Epi& ep
       tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc) * kTileN +
                               (static_cast<uint32_t>(quarter * 32) << 16);
+      epi.tile_begin(row, sh->colvec[acc]);
 #pragma unroll 1
       for (int c0 = half * (kTileN / 2); c0 < (half + 1) * (kTileN / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_addr + c0, r);
         tmem_wait_ld();
-        epi.chunk(row, r, sh->colvec[acc], c0, ct * kTileN + c0, b_row0 + c0, scratch, -__builtin_huge_valf(), __builtin_huge_valf());
+        epi.template chunk<false>(row, r, sh->colvec[acc], c0, ct * kTileN + c0, b_row0 + c0, scratch, -__builtin_huge_valf(), __builtin_huge_valf());
       }
       tc_fence_before();
       __syncwarp();

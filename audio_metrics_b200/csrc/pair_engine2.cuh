@@ -379,14 +379,16 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
         tc_fence_after();
         const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc) * kTileN +
                                 (static_cast<uint32_t>(quarter * 32) << 16);
+        epi.tile_begin(row, sh->colvec[q]);
 #pragma unroll 1
         for (int c0 = half * (kTileN / 2); c0 < (half + 1) * (kTileN / 2); c0 += 32) {
           uint32_t r[32];
           tmem_ld32(t_addr + c0, r);
+          // the chunk's staged scalars: loaded while the TMEM load is in flight
+          const float cmin = Epi::kChunkMin ? sh->cvmin[q][c0 >> 5] : -__builtin_huge_valf();
+          const float cmax = Epi::kChunkMin ? sh->cvmax[q][c0 >> 5] : __builtin_huge_valf();
           tmem_wait_ld();
-          epi.chunk(row, r, sh->colvec[q], c0, ct * kTileN + c0, b_row0 + c0, scratch,
-                    epi.cmin_ptr() ? sh->cvmin[q][c0 >> 5] : -__builtin_huge_valf(),
-                    epi.cmax_ptr() ? sh->cvmax[q][c0 >> 5] : __builtin_huge_valf());
+          epi.template chunk<Epi::kChunkMin>(row, r, sh->colvec[q], c0, ct * kTileN + c0, b_row0 + c0, scratch, cmin, cmax);
         }
         tc_fence_before();
         __syncwarp();

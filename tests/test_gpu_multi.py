@@ -39,7 +39,11 @@ def _worker(rank, world, port, n_ref, n_cand, d, k, out):
         a = evaluate_containers(R, C, ("fad", "kd", "prdc"), nearest_k=k, kd_subsets=12, kd_subset_size=200)
         b = evaluate_sharded(torch.from_numpy(ref[r0:r0 + rn]).to(dev), torch.from_numpy(cand[c0:c0 + cn]).to(dev),
                              n_ref, n_cand, nearest_k=k, kd_subsets=12, kd_subset_size=200)
+        # PCA fitted on each rank's rows: the statistics are reduced over the ranks first (dist.global_stats)
+        from audio_metrics_b200.projection import IncrementalPCA
+        pca = IncrementalPCA(n_components=16, device=dev).fit(R)
         out[rank] = (a, b)
+        out[f"pca{rank}"] = (pca.components_.cpu().numpy(), pca.singular_values_.cpu().numpy(), pca.n_samples_seen_)
     finally:
         dist.destroy_process_group()
 
@@ -69,6 +73,13 @@ def test_two_ranks_equal_one(cuda_device, n_ref, n_cand):
                 assert got[key] == pytest.approx(want[key], rel=1e-9), key
             for key in ("precision", "recall", "density", "coverage"):
                 assert got[key] == want[key], key      # ratios of exact integer counts: identical
+    from audio_metrics_b200.projection import IncrementalPCA
+    pca = IncrementalPCA(n_components=16).fit(R)
+    for rank in range(world):
+        comp, sv, seen = out[f"pca{rank}"]
+        assert seen == n_ref
+        np.testing.assert_allclose(sv, pca.singular_values_.cpu().numpy(), rtol=1e-10)
+        np.testing.assert_allclose(comp, pca.components_.cpu().numpy(), atol=1e-7)
 
 
 def test_in_process_devices_equal_one(cuda_device):
