@@ -33,6 +33,7 @@ struct DumpEpi {
     r.sum = 0.f;
   }
   __device__ void tile_begin(Row&, const float (*)[kTileN]) const {}
+  __device__ void tile_end(Row&, float*) const {}
   template <bool>
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
                         long long b_row0, float*, float, float) const {
@@ -101,6 +102,7 @@ struct KdEpi {
     }
   }
   __device__ void tile_begin(Row&, const float (*)[kTileN]) const {}
+  __device__ void tile_end(Row&, float*) const {}
   template <bool>
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0,
                         int col0, long long b_row0, float*, float, float) const {
@@ -198,7 +200,8 @@ struct TopkEpi {
   // lists together then take about as many insertions as one list over all columns would.
   // The refine kernel's certificate is unaffected: whatever a list rejected was >= some list's
   // K-th key at that time >= that list's final K-th key >= the K-th smallest of the union.
-  struct Row { float m2isr, sc; float v[K]; int c[K]; float* mine; const volatile float* peer; };
+  struct Row { float m2isr, sc; float v[K]; int c[K]; float* mine; const volatile float* peer; int qn; };
+  static constexpr int kQueue = 4;   // (key, column) pairs a thread can park: 8 of its kScratchFloats
   __device__ const float* colvec_ptr(int v) const { return v == 0 ? inv_b : norm_b; }
   __device__ const float* cmin_ptr() const { return cmin_b; }
   __device__ const float* cmax_ptr() const { return nullptr; }
@@ -209,6 +212,7 @@ struct TopkEpi {
     r.mine = xchg + half;
     r.peer = xchg + (half ^ 1);
     *r.mine = kInf;
+    r.qn = 0;
   }
   // Sorted insert with no dependent chain: slot i of the new list is old slot i-1 if the key goes
   // in front of it, the key itself if it lands here, old slot i otherwise — every slot from the OLD
@@ -256,10 +260,14 @@ struct TopkEpi {
     // private shared-memory slots, and the warp loops while any lane still has a bit to consume
     // (usually one trip): a lane picks its lowest set column, reloads that key by dynamic index and
     // inserts it; the list's last key tightens as it goes.
-    // The groups are walked by a run-time loop (the warp-uniform switch moves the group's eight
-    // accumulators into fixed registers) so that the slow path exists once, not four times: the
-    // whole chunk loop then stays inside the instruction cache of the scheduler, and the far jumps
-    // around four unrolled copies cost more than the eight moves.
+    // Candidates are only PARKED here — (key, column) pairs in the thread's shared-memory slots — and
+    // inserted by drain() once the engine has handed the accumulator back to the MMA warp
+    // (tile_end).  Measured: the scan alone never delays the next tile, the inserts did — a warp
+    // that met candidates in several chunks of one tile held the accumulator (and through the pair
+    // barrier both CTAs' tensor pipes) beyond the tile period, while on average the epilogue warps
+    // idle 40 % of the time.  The groups are walked by a run-time loop (the warp-uniform switch
+    // moves the group's eight accumulators into fixed registers) so that this code exists once,
+    // not four times: the whole chunk loop stays inside the scheduler's instruction cache.
     unsigned todo = __reduce_or_sync(0xffffffffu, gm);
 #pragma unroll 1
     while (todo) {
@@ -284,8 +292,6 @@ struct TopkEpi {
           for (int j = 0; j < 8; ++j) a[j] = f32(acc[24 + j]);
           break;
       }
-      // all loads before the stores: the scratch slots could alias the column vectors as far as the
-      // compiler knows, and a load held behind each store pays the shared-memory latency 8 times
       const float4 na = *reinterpret_cast<const float4*>(&cv[1][c0 + 8 * h]);
       const float4 nb = *reinterpret_cast<const float4*>(&cv[1][c0 + 8 * h + 4]);
       float t[8];
@@ -297,28 +303,46 @@ struct TopkEpi {
       t[5] = fmaf(a[5], sc, nb.y);
       t[6] = fmaf(a[6], sc, nb.z);
       t[7] = fmaf(a[7], sc, nb.w);
-      unsigned mask = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) mask |= (t[j] < thr) ? (1u << j) : 0u;
-      if (!__any_sync(0xffffffffu, mask != 0)) continue;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) scratch[j] = t[j];   // stride-9 slots: scalar stores, conflict-free
       const int col0 = static_cast<int>(b_row0) + 8 * h;
+      unsigned pend = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pend |= (t[j] < thr) ? (1u << j) : 0u;
+      // Park them.  If some thread has more than fit (the first tiles of an item, when the list is
+      // still filling), everybody inserts what is parked first and the loop goes round again.
+      bool again;
 #pragma unroll 1
       do {
-        float key = kInf;
-        int col = -1;
-        if (mask) {
-          const int j = __ffs(mask) - 1;
-          mask &= mask - 1;
-          key = scratch[j];
-          col = col0 + j;
+        again = __any_sync(0xffffffffu, r.qn + __popc(pend) > kQueue);
+        if (again) drain(r, scratch);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (((pend >> j) & 1u) && r.qn < kQueue) {
+            scratch[2 * r.qn] = t[j];
+            scratch[2 * r.qn + 1] = __int_as_float(col0 + j);
+            ++r.qn;
+            pend &= ~(1u << j);
+          }
         }
-        insert(r, key, col);
-      } while (__any_sync(0xffffffffu, mask != 0));
+      } while (again && __any_sync(0xffffffffu, pend != 0));
     }
+  }
+  // Insert everything parked by chunk(); the warp loops while any lane has an entry left.
+  __device__ __forceinline__ void drain(Row& r, const float* scratch) const {
+    if (!__any_sync(0xffffffffu, r.qn != 0)) return;
+#pragma unroll 1
+    do {
+      float key = kInf;
+      int col = -1;
+      if (r.qn) {
+        --r.qn;
+        key = scratch[2 * r.qn];
+        col = __float_as_int(scratch[2 * r.qn + 1]);
+      }
+      insert(r, key, col);
+    } while (__any_sync(0xffffffffu, r.qn != 0));
     *r.mine = r.v[K - 1];
   }
+  __device__ void tile_end(Row& r, float* scratch) const { drain(r, scratch); }
   __device__ void row_end(Row& r, const ItemCoord& c, int, long long a_row, int, int, int half) const {
     const long long o = (static_cast<long long>(2 * c.split + half) * list_rows + (a_row - a_row_base)) * K;
 #pragma unroll
@@ -377,6 +401,7 @@ struct CountEpi {
     if (pos < list_cap) list[pos] = PairEntry{i, j_kind};
   }
   __device__ void tile_begin(Row& r, const float (*cv)[kTileN]) const { r.sc = cv[0][0] * r.m2isr; }
+  __device__ void tile_end(Row&, float*) const {}
   template <bool kStaged>
   __device__ void chunk(Row& r, const uint32_t (&acc)[32], const float (*cv)[kTileN], int c0, int,
                         long long b_row0, float*, float cmin, float cmax) const {

@@ -170,6 +170,7 @@ __device__ __forceinline__ void epilogue_role(const EngineGeom& g, const Epi& ep
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
+      epi.tile_end(row, scratch);
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1;
     }

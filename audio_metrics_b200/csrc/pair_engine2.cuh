@@ -396,6 +396,7 @@ pair_engine2_kernel(const EngineGeom g, const Epi epi) {
           mbar_arrive(&sh->cv_empty[q]);
           mbar_arrive_cluster(acc == 0 ? l_pair_empty0 : l_pair_empty1);
         }
+        epi.tile_end(row, scratch);   // work that does not need the accumulator: after it is handed back
         ++tile;
         acc ^= 1;
         if (acc == 0) acc_ph ^= 1;
