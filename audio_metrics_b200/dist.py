@@ -27,6 +27,7 @@ with stand-in kernels; the product ``CudaOps`` calls the C ABI and nothing else.
 from __future__ import annotations
 
 import functools
+import os
 
 import numpy as np
 import torch
@@ -115,6 +116,7 @@ def _gather_meta(values, device, group):
 # Cholesky + 69 fp64 GEMMs of d^3: 3.8 ms at d = 512 on a B200) that only one rank needs to do; that
 # rank gets a proportionally smaller share of the all-pairs sweeps so that all ranks finish together.
 FAD_RANK = 0
+FAD_SIDE_STREAM = os.environ.get("AMB_FAD_SIDE", "1") != "0"   # A/B switch of the side-stream placement
 
 
 def fad_seconds(d: int) -> float:
@@ -474,15 +476,16 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
             pending["_mom"] = mom
         lookup = lambda s: stats[[t is s for t in stat_sets].index(True)]
         pairs = [(lookup(x), lookup(y)) for _, x, y in fad_pairs]
-        if world == 1:
-            pending["fad"] = ops.frechet_batch(pairs)
-        elif rank == FAD_RANK:
+        if rank == FAD_RANK:
             # N-independent work: ONE rank computes it.  That rank sweeps fewer rows (work_weights), so it
             # reaches every collective of the sweeps early; the Frechet kernels run on a side stream and
-            # fill exactly those waits instead of holding all ranks up at the next collective.
-            if mom.is_cuda:
-                side = _side_stream(mom.device)
-                side.wait_stream(torch.cuda.current_stream(mom.device))
+            # fill exactly those waits instead of holding all ranks up at the next collective.  On one GPU
+            # the same side stream fills the tails of the persistent sweeps (the last partial round of
+            # work items leaves SMs idle) with the small, latency-bound Frechet kernels.
+            sdev = torch.device(stats[0][0].device if isinstance(stats[0], (tuple, list)) else tdev)
+            if sdev.type == "cuda" and (want_prdc or want_kd) and FAD_SIDE_STREAM:
+                side = _side_stream(sdev)
+                side.wait_stream(torch.cuda.current_stream(sdev))
                 with torch.cuda.stream(side):
                     pending["fad"] = ops.frechet_batch(pairs)
                 pending["_fad_side"] = side
@@ -547,9 +550,9 @@ def _fused(ops, ref, cand, metrics, nearest_k, group, extra_fad=(), kd_subsets=1
 
     # ---- the one read-back
     result = {}
+    if "_fad_side" in pending:
+        torch.cuda.current_stream(pending["fad"].device).wait_stream(pending["_fad_side"])
     if fad_pairs and world > 1:
-        if "_fad_side" in pending:
-            torch.cuda.current_stream(pending["fad"].device).wait_stream(pending["_fad_side"])
         dist.broadcast(pending["fad"], src=dist.get_global_rank(group, FAD_RANK) if group is not None else FAD_RANK,
                        group=group)
         _mark("Frechet distances joined, broadcast", tdev)
