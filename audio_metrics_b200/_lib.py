@@ -16,7 +16,8 @@ import os as _os
 _LIB_PATH = Path(_os.environ.get("AMB200_LIB") or Path(__file__).resolve().parent / "libamb200.so")
 _lib = None
 
-AMB_F32, AMB_F64 = 0, 1
+AMB_F32, AMB_F64, AMB_I32, AMB_I64, AMB_U8 = 0, 1, 2, 3, 4
+AMB_SUM, AMB_MAX = 0, 1
 AMB_KERNEL_POLY, AMB_KERNEL_RBF = 0, 1
 AMB_MMD_UNBIASED, AMB_MMD_BIASED, AMB_MMD_USTAT, AMB_MMD_UNIT_DIAGONAL = 0, 1, 2, 4
 AMB_ERR_ARG, AMB_ERR_CUDA, AMB_ERR_WS, AMB_ERR_NUMERIC = -1, -2, -3, -4
@@ -63,6 +64,14 @@ SIGNATURES = {
     "amb_host_knn_radii": (_i, [_i, _vp, _i, _ll, _i, _i, _vp]),
     "amb_host_prdc": (_i, [_i, _vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "amb_host_evaluate": (_i, [_vp, _i, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "amb_comm_init": (_i, [_vp, _i, _vp]),
+    "amb_comm_size": (_i, [_vp]),
+    "amb_comm_device": (_i, [_vp, _i]),
+    "amb_comm_group_begin": (_i, []),
+    "amb_comm_group_end": (_i, []),
+    "amb_comm_allreduce": (_i, [_vp, _i, _vp, _vp, _ll, _i, _i, _vp]),
+    "amb_comm_allgather": (_i, [_vp, _i, _vp, _vp, _ll, _i, _vp]),
+    "amb_comm_destroy": (_i, [_vp]),
     "amb_debug_dot_matrix": (_i, [_i, _vp, _vp, _ll, _vp, _ll, _i, _vp, _ll, C.c_uint, C.c_uint]),
 }
 

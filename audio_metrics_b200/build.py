@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG.parent / "build" / "obj"
 LIB = PKG / "libamb200.so"
-SOURCES = ["common.cu", "pack.cu", "prdc.cu", "kd.cu", "cov.cu", "cov_tc.cu", "fad.cu", "pca.cu", "host.cu"]
+SOURCES = ["common.cu", "pack.cu", "prdc.cu", "kd.cu", "cov.cu", "cov_tc.cu", "fad.cu", "pca.cu", "host.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
@@ -56,7 +56,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     tmp = LIB.with_suffix(".so.tmp")
-    cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

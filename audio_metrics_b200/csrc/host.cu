@@ -5,6 +5,7 @@
 // the reference's metric functions calls directly.
 #include <condition_variable>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -101,9 +102,8 @@ struct EvalShared {
   // inputs
   const void* ref; const void* cand; long long n, m; int d, dtype, k;
   const int32_t* kd_idx; int S, msub; int want_fad; int n_dev;
-  // exchanged between the devices through host memory
-  std::vector<float> r_ref, r_cand;
-  std::vector<long long> totals;      // [n_dev][4]
+  amb_comm_t* comm = nullptr;         // n_dev > 1: the exchanges between the devices (amb_comm_*)
+  std::vector<long long> totals;      // [n_dev][4]: hits, sum of counts (device 0's are used), rows recalled, rows covered
   double fad = 0, kd[2] = {0, 0};
   std::vector<int> rc;
   std::vector<std::string> err;
@@ -167,8 +167,13 @@ static void eval_worker(EvalShared* sh, ThreadBarrier* bar, int rank, int dev) {
       even_rows(m, sh->n_dev, rank, &c0, &cn);
       pR = h.alloc<uint8_t>(amb_packed_bytes(n, d));
       pC = h.alloc<uint8_t>(amb_packed_bytes(m, d));
-      rR = h.alloc<float>(n);
-      rC = h.alloc<float>(m);
+      // radii buffers padded to whole shards: the allgather moves equal counts per device
+      long long chunk_r = 0, chunk_c = 0, tmp0 = 0;
+      even_rows(n, sh->n_dev, 0, &tmp0, &chunk_r);
+      even_rows(m, sh->n_dev, 0, &tmp0, &chunk_c);
+      if (sh->n_dev == 1) { chunk_r = n; chunk_c = m; }
+      rR = h.alloc<float>(static_cast<size_t>(chunk_r) * sh->n_dev);
+      rC = h.alloc<float>(static_cast<size_t>(chunk_c) * sh->n_dev);
       wsb = amb_knn_ws_bytes(rn, n, d, k);
       const size_t w2 = amb_knn_ws_bytes(cn, m, d, k), w3 = amb_prdc_ws_bytes(n, m);
       wsb = wsb > w2 ? wsb : w2;
@@ -179,26 +184,28 @@ static void eval_worker(EvalShared* sh, ThreadBarrier* bar, int rank, int dev) {
         h.run(amb_pack(dev, h.st, dC, dtype, m, d, d, pC));
         h.run(amb_knn_radii(dev, h.st, dR, dtype, d, pR, n, d, r0, rn, k, rR + r0, nullptr, ws, wsb));
         h.run(amb_knn_radii(dev, h.st, dC, dtype, d, pC, m, d, c0, cn, k, rC + c0, nullptr, ws, wsb));
-        h.download(sh->r_ref.data() + r0, rR + r0, static_cast<size_t>(rn));
-        h.download(sh->r_cand.data() + c0, rC + c0, static_cast<size_t>(cn));
       }
     }
     if (fad_dev) h.download(&sh->fad, fad_dev, 1);
     if (kd_dev) h.download(sh->kd, kd_dev, 2);
     h.finish();
     if (h.rc) { fail(h.rc); alive = false; }
-    bar->wait();                                    // every device's radii slices are in host memory
+    bar->wait();                                    // every device got this far (or reported why not)
     for (int q = 0; q < sh->n_dev; ++q) alive = alive && sh->rc[q] == AMB_OK;
+    // ---- every device's radii slices to every device: in-place allgather over NVLink
+    if (alive && want_prdc && sh->n_dev > 1) {
+      long long chunk_r = 0, chunk_c = 0, tmp0 = 0;
+      even_rows(n, sh->n_dev, 0, &tmp0, &chunk_r);
+      even_rows(m, sh->n_dev, 0, &tmp0, &chunk_c);
+      h.run(amb_comm_allgather(sh->comm, rank, rR + chunk_r * rank, rR, chunk_r, AMB_F32, h.st));
+      h.run(amb_comm_allgather(sh->comm, rank, rC + chunk_c * rank, rC, chunk_c, AMB_F32, h.st));
+    }
     // ---- counts of this device's reference rows against all candidates
     if (alive && want_prdc) {
       int32_t* col = h.alloc<int32_t>(m);
       uint8_t* rec = h.alloc<uint8_t>(rn ? rn : 1);
       uint8_t* cov = h.alloc<uint8_t>(rn ? rn : 1);
       long long* totals = h.alloc<long long>(8);
-      if (!h.rc) {
-        h.rc = check_cuda(cudaMemcpyAsync(rR, sh->r_ref.data(), static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h.st), "H2D");
-        if (!h.rc) h.rc = check_cuda(cudaMemcpyAsync(rC, sh->r_cand.data(), static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, h.st), "H2D");
-      }
       long long t[8] = {0};
       void* big = nullptr;
       // the overflow ladder of amb200.h: default list -> list of the reported size -> exhaustive kernel
@@ -212,10 +219,7 @@ static void eval_worker(EvalShared* sh, ThreadBarrier* bar, int rank, int dev) {
                                 amb_prdc_ws_bytes_cap(n, m, t[4])));
         else
           h.run(amb_prdc_counts_exact(dev, h.st, dR, d, n, rR, dC, d, m, rC, d, dtype, r0, rn, col, rec, cov));
-        // per-device partial numerators: sum of counts and row flags (the "columns with a hit" count
-        // needs the column vector summed over devices first, done on the host below)
-        h.run(amb_prdc_reduce(dev, h.st, nullptr, 0, rec, cov, rn, totals));
-        h.download(t, totals, 8);
+        h.download(t, totals, 8);                   // t[4]: near-tie pairs this device met
         h.finish();
         if (h.rc) break;
         const long long cap = attempt == 0 ? amb_prdc_ws_list_cap(n, m, wsb) : t[4];
@@ -230,18 +234,23 @@ static void eval_worker(EvalShared* sh, ThreadBarrier* bar, int rank, int dev) {
           (void)cudaGetLastError();
         }
       }
-      if (!h.rc) {   // column counts of this shard -> host, summed by the caller
-        std::vector<int32_t> hc(static_cast<size_t>(m));
-        h.download(hc.data(), col, static_cast<size_t>(m));
+      // ---- per-candidate counts summed over the devices (allreduce), then the four numerators.
+      // A device that failed must not leave the others waiting inside the collective: agree first.
+      if (h.rc) fail(h.rc);
+      if (sh->n_dev > 1) {
+        bar->wait();
+        bool all_ok = true;
+        for (int q = 0; q < sh->n_dev; ++q) all_ok = all_ok && sh->rc[q] == AMB_OK;
+        if (!all_ok) return;
+        h.run(amb_comm_allreduce(sh->comm, rank, col, col, m, AMB_I32, AMB_SUM, h.st));
+      }
+      if (!h.rc) {
+        h.zero(totals, 32);
+        h.run(amb_prdc_reduce(dev, h.st, col, m, rec, cov, rn, totals));
+        h.download(t, totals, 4);
         h.finish();
-        if (!h.rc) {
-          static std::mutex mu;
-          std::lock_guard<std::mutex> lk(mu);
-          int32_t* acc = reinterpret_cast<int32_t*>(sh->totals.data() + 4 * sh->n_dev);   // [m] int32 after the per-device slots
-          for (long long j = 0; j < m; ++j) acc[j] += hc[j];
-          sh->totals[4 * rank + 2] = t[2];
-          sh->totals[4 * rank + 3] = t[3];
-        }
+        if (!h.rc)
+          for (int q = 0; q < 4; ++q) sh->totals[4 * rank + q] = t[q];
       }
       if (h.rc) fail(h.rc);
     }
@@ -405,16 +414,27 @@ int amb_host_evaluate(const int* devs, int n_dev, const void* ref, long long n, 
   EvalShared sh;
   sh.ref = ref; sh.cand = cand; sh.n = n; sh.m = m; sh.d = d; sh.dtype = dtype; sh.k = k;
   sh.kd_idx = kd_idx; sh.S = S; sh.msub = msub; sh.want_fad = want_fad; sh.n_dev = n_dev;
-  if (k > 0) {
-    sh.r_ref.resize(static_cast<size_t>(n));
-    sh.r_cand.resize(static_cast<size_t>(m));
-  }
-  // [n_dev][4] per-device totals, followed by the summed per-candidate counts ([m] int32)
-  sh.totals.assign(static_cast<size_t>(4 * n_dev) + static_cast<size_t>((m + 1) / 2), 0);
+  sh.totals.assign(static_cast<size_t>(4 * n_dev), 0);
   sh.rc.assign(n_dev, AMB_OK);
   sh.err.assign(n_dev, std::string());
   const int workers = k > 0 ? n_dev : 1;          // without PRDC everything is N-independent: one device
   sh.n_dev = workers;
+  if (workers > 1) {
+    // one set of communicators per device list, created on first use and kept (ncclCommInitAll
+    // costs a few hundred milliseconds)
+    static std::mutex mu;
+    static std::map<std::vector<int>, amb_comm_t*> comms;
+    std::lock_guard<std::mutex> lk(mu);
+    const std::vector<int> key(devs, devs + workers);
+    auto it = comms.find(key);
+    if (it == comms.end()) {
+      amb_comm_t* c = nullptr;
+      const int rc = amb_comm_init(devs, workers, &c);
+      if (rc) return rc;
+      it = comms.emplace(key, c).first;
+    }
+    sh.comm = it->second;
+  }
   ThreadBarrier bar(workers);
   std::vector<std::thread> th;
   for (int r = 0; r < workers; ++r) th.emplace_back(eval_worker, &sh, &bar, r, devs[r]);
@@ -426,9 +446,10 @@ int amb_host_evaluate(const int* devs, int n_dev, const void* ref, long long n, 
   if (want_fad) out[0] = sh.fad;
   if (kd_idx) { out[1] = sh.kd[0]; out[2] = sh.kd[1]; }
   if (k > 0) {
-    const int32_t* col = reinterpret_cast<const int32_t*>(sh.totals.data() + 4 * workers);
-    long long hits = 0, total = 0, recalled = 0, covered = 0;
-    for (long long j = 0; j < m; ++j) { hits += col[j] > 0; total += col[j]; }
+    // hits and the sum of counts come from the reduced column vector (the same on every device);
+    // the row flags belong to each device's own reference rows
+    const long long hits = sh.totals[0], total = sh.totals[1];
+    long long recalled = 0, covered = 0;
     for (int r = 0; r < workers; ++r) { recalled += sh.totals[4 * r + 2]; covered += sh.totals[4 * r + 3]; }
     out[3] = static_cast<double>(hits) / static_cast<double>(m);                                        // prdc.py:36-38
     out[4] = static_cast<double>(recalled) / static_cast<double>(n);                                    // prdc.py:40-42

@@ -34,7 +34,7 @@ extern "C" {
 
 typedef void* amb_stream_t; /* a cudaStream_t (0 = legacy default stream) */
 
-enum { AMB_F32 = 0, AMB_F64 = 1 };
+enum { AMB_F32 = 0, AMB_F64 = 1, AMB_I32 = 2, AMB_I64 = 3, AMB_U8 = 4 }; /* the integer codes: amb_comm_* only */
 enum {
   AMB_OK = 0,
   AMB_ERR_ARG = -1,     /* invalid argument (shape, dtype, k, null pointer) */
@@ -245,9 +245,11 @@ int amb_host_prdc(int dev, const void* ref, long long n, const void* cand, long 
  * host arrays, sharded over the n_dev devices of devs[] inside this process (one worker thread per
  * device — the reference's multi-GPU mechanism is threads in one process too,
  * util/gpu_parallel.py:20-76): every device uploads the rows once, takes a 256-aligned row shard of
- * both all-pairs sweeps against all columns, and exchanges radii slices and per-candidate counts
- * through host memory; statistics, the Frechet distance and the kernel distance run on devs[0]
- * behind its uploads.  No NCCL, no process group.
+ * both all-pairs sweeps against all columns, and exchanges radii slices (allgather) and
+ * per-candidate counts (allreduce) with amb_comm_* on the device (communicators are created on the
+ * first call with a device list and kept for the life of the process); statistics, the Frechet
+ * distance and the kernel distance run on devs[0] behind its uploads.  No process group; with
+ * n_dev == 1 no NCCL either.
  *   want_fad != 0           out[0] = Frechet distance of (candidate, reference)
  *   kd_idx != NULL          out[1], out[2] = kernel_distance_mean / _std; kd_idx [S, 2, msub] int32 as
  *                           amb_kd_subsets (drawn for features_1 = candidate, features_2 = reference)
@@ -256,6 +258,31 @@ int amb_host_prdc(int dev, const void* ref, long long n, const void* cand, long 
 int amb_host_evaluate(const int* devs, int n_dev, const void* ref, long long n, const void* cand,
                       long long m, int d, int dtype, int k, const int32_t* kd_idx, int S, int msub,
                       int want_fad, double* out);
+
+/* ------------------------------------------------------------------ collectives
+ * The exchanges between row shards (allreduce of fp64 moments, allgather of radii
+ * slices, allreduce of per-candidate counts) for a caller that holds device pointers on several
+ * GPUs of ONE process — the reference's multi-GPU model (threads of one process,
+ * util/gpu_parallel.py:20-76).  amb_comm_init creates one NCCL communicator per listed device
+ * (ncclCommInitAll); `rank` is the position in devs[].  Every call is asynchronous on the given
+ * stream of that rank's device.  Either one host thread per rank calls its own rank, or one thread
+ * issues all ranks between amb_comm_group_begin / _end.  In place: send == recv for allreduce,
+ * send == recv + rank * count_per_rank * sizeof(dtype) for allgather.
+ * NCCL is bound at run time (libnccl.so.2, shared with a PyTorch already in the process); without
+ * it amb_comm_init returns AMB_ERR_CUDA and nothing else in the library is affected.
+ * amb_host_evaluate with n_dev > 1 uses exactly these calls. */
+typedef struct amb_comm amb_comm_t;
+enum { AMB_SUM = 0, AMB_MAX = 1 };
+int amb_comm_init(const int* devs, int n_dev, amb_comm_t** comm);
+int amb_comm_size(const amb_comm_t* comm);
+int amb_comm_device(const amb_comm_t* comm, int rank);
+int amb_comm_group_begin(void);
+int amb_comm_group_end(void);
+int amb_comm_allreduce(amb_comm_t* comm, int rank, const void* send, void* recv, long long count,
+                       int dtype, int op, amb_stream_t stream);
+int amb_comm_allgather(amb_comm_t* comm, int rank, const void* send, void* recv,
+                       long long count_per_rank, int dtype, amb_stream_t stream);
+int amb_comm_destroy(amb_comm_t* comm);
 
 /* ------------------------------------------------------------- debug / validation
  * Full dot-product matrix through the tensor-core engine (small sizes only):

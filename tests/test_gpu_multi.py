@@ -116,3 +116,52 @@ def test_in_process_devices_equal_one(cuda_device):
         am.add_reference(audio_ref)
         res.append(am.evaluate(audio_cand))
     assert res[0] == res[1]
+
+
+def test_comm_two_devices(cuda_device):
+    """amb_comm_* over two GPUs of this process, all ranks issued by one thread between group_begin /
+    group_end: in-place allreduce (sum of int32 counts, max of int64, sum of fp64 moments) and the in-place
+    allgather of radii slices — the exchanges of the sharded sweeps."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import ctypes as C
+    from audio_metrics_b200 import _lib
+    L = _lib.lib()
+    comm = C.c_void_p()
+    devs = (C.c_int * 2)(0, 1)
+    _lib.check(L.amb_comm_init(devs, 2, C.byref(comm)))
+    try:
+        assert L.amb_comm_size(comm) == 2
+        d = [torch.device("cuda", i) for i in range(2)]
+        g = torch.Generator().manual_seed(5)
+        counts = [torch.randint(0, 9, (12345,), generator=g, dtype=torch.int32) for _ in d]
+        mom = [torch.randn(4097, generator=g, dtype=torch.float64) for _ in d]
+        mx = [torch.randint(0, 1 << 40, (3,), generator=g, dtype=torch.int64) for _ in d]
+        radii = torch.rand(2 * 768, generator=g)
+        c_dev = [c.to(x) for c, x in zip(counts, d)]
+        m_dev = [c.to(x) for c, x in zip(mom, d)]
+        x_dev = [c.to(x) for c, x in zip(mx, d)]
+        r_dev = []
+        for i, x in enumerate(d):
+            buf = torch.full((2 * 768,), -1.0, device=x)
+            buf[768 * i:768 * (i + 1)] = radii[768 * i:768 * (i + 1)].to(x)
+            r_dev.append(buf)
+        for x in d:
+            torch.cuda.synchronize(x)
+        st = [_lib.stream_ptr(x) for x in d]
+        _lib.check(L.amb_comm_group_begin())
+        for i in range(2):
+            _lib.check(L.amb_comm_allreduce(comm, i, c_dev[i].data_ptr(), c_dev[i].data_ptr(), 12345, _lib.AMB_I32, _lib.AMB_SUM, st[i]))
+            _lib.check(L.amb_comm_allreduce(comm, i, m_dev[i].data_ptr(), m_dev[i].data_ptr(), 4097, _lib.AMB_F64, _lib.AMB_SUM, st[i]))
+            _lib.check(L.amb_comm_allreduce(comm, i, x_dev[i].data_ptr(), x_dev[i].data_ptr(), 3, _lib.AMB_I64, _lib.AMB_MAX, st[i]))
+            _lib.check(L.amb_comm_allgather(comm, i, r_dev[i].data_ptr() + 4 * 768 * i, r_dev[i].data_ptr(), 768, _lib.AMB_F32, st[i]))
+        _lib.check(L.amb_comm_group_end())
+        for x in d:
+            torch.cuda.synchronize(x)
+        for i in range(2):
+            assert torch.equal(c_dev[i].cpu(), counts[0] + counts[1])
+            assert torch.equal(m_dev[i].cpu(), mom[0] + mom[1])          # two addends: order-independent
+            assert torch.equal(x_dev[i].cpu(), torch.maximum(mx[0], mx[1]))
+            assert torch.equal(r_dev[i].cpu(), radii)
+    finally:
+        _lib.check(L.amb_comm_destroy(comm))

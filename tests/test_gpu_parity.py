@@ -301,3 +301,33 @@ def test_host_evaluate_one_call(cuda_device):
     _lib.check(L.amb_host_evaluate(devs, 1, ref.ctypes.data, 3100, cand.ctypes.data, 2700, 96, 0, 0, None, 0, 0, 1, out))
     assert out[0] == pytest.approx(want["fad"], rel=1e-12) and all(np.isnan(v) for v in list(out)[1:])
     assert L.amb_host_evaluate(devs, 1, ref.ctypes.data, 3, cand.ctypes.data, 2700, 96, 0, 5, None, 0, 0, 1, out) == _lib.AMB_ERR_ARG
+
+
+def test_comm_single_device(cuda_device):
+    """amb_comm_*: a communicator over one device — allreduce and allgather are identities, argument
+    errors are reported, NCCL is bound at run time (the library itself does not link it)."""
+    import ctypes as C
+    L = _lib.lib()
+    comm = C.c_void_p()
+    devs = (C.c_int * 1)(0)
+    _lib.check(L.amb_comm_init(devs, 1, C.byref(comm)))
+    try:
+        assert L.amb_comm_size(comm) == 1 and L.amb_comm_device(comm, 0) == 0 and L.amb_comm_device(comm, 1) == -1
+        dev = torch.device("cuda", 0)
+        st = _lib.stream_ptr(dev)
+        x = torch.arange(1000, dtype=torch.float64, device=dev)
+        y = torch.empty_like(x)
+        _lib.check(L.amb_comm_allreduce(comm, 0, x.data_ptr(), y.data_ptr(), 1000, _lib.AMB_F64, _lib.AMB_SUM, st))
+        c = torch.arange(77, dtype=torch.int32, device=dev)
+        _lib.check(L.amb_comm_allreduce(comm, 0, c.data_ptr(), c.data_ptr(), 77, _lib.AMB_I32, _lib.AMB_MAX, st))
+        g = torch.empty(50, dtype=torch.float32, device=dev)
+        src = torch.randn(50, device=dev)
+        _lib.check(L.amb_comm_allgather(comm, 0, src.data_ptr(), g.data_ptr(), 50, _lib.AMB_F32, st))
+        torch.cuda.synchronize()
+        assert torch.equal(x, y) and torch.equal(c, torch.arange(77, dtype=torch.int32, device=dev)) and torch.equal(g, src)
+        assert L.amb_comm_allreduce(comm, 1, x.data_ptr(), y.data_ptr(), 10, _lib.AMB_F64, _lib.AMB_SUM, st) == _lib.AMB_ERR_ARG
+        assert L.amb_comm_allreduce(comm, 0, x.data_ptr(), y.data_ptr(), 10, 99, _lib.AMB_SUM, st) == _lib.AMB_ERR_ARG
+    finally:
+        _lib.check(L.amb_comm_destroy(comm))
+    two = (C.c_int * 2)(0, 0)
+    assert L.amb_comm_init(two, 2, C.byref(comm)) == _lib.AMB_ERR_ARG
