@@ -11,12 +11,19 @@
 // without NCCL, a process that already holds an NCCL (PyTorch's) shares it, and the first
 // amb_comm_init fails loudly where there is none.
 #include <dlfcn.h>
-#include <nccl.h>
 
 #include <mutex>
 #include <vector>
 
 #include "internal.cuh"
+
+// The slice of nccl.h this file needs (NCCL 2.x ABI: opaque communicator, C enums), declared here so
+// that building the library does not need NCCL's headers either.
+typedef struct ncclComm* ncclComm_t;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5,
+               ncclFloat16 = 6, ncclFloat32 = 7, ncclFloat64 = 8 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
 
 namespace amb {
 
