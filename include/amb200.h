@@ -1,7 +1,7 @@
 /* amb200 — C ABI of the B200-native embedding-set distance path.
  *
  * The reference (SonyCSLParis/audio-metrics, pure Python) has no FFI layer: its
- * boundary for this path is the Python call surface of data.py / metrics/*.py.
+ * boundary for this path is the Python call surface of data.py and the modules under metrics/.
  * Each entry point below is what a binding for one of those functions calls; the
  * reference interface it replaces is cited as  file:line  (relative to the
  * reference's src/audio_metrics/).

@@ -69,3 +69,23 @@ def test_argument_errors_are_value_errors():
     assert L.amb_host_stats(0, None, 0, 8, 4, None, None) == _lib.AMB_ERR_ARG
     with pytest.raises(ValueError):
         _lib.check(_lib.AMB_ERR_ARG)
+
+
+def test_header_is_c_and_links_from_c(tmp_path):
+    """include/amb200.h compiles as C99 and a plain C program linked against libamb200.so runs the
+    host-only entry points (tests/c/abi_smoke.c) — the binding a cgo / JNI / ctypes caller relies on."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = Path(__file__).resolve().parents[1]
+    _lib.lib()
+    lib = Path(_lib._LIB_PATH)
+    exe = tmp_path / "abi_smoke"
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", str(root / "include"), str(root / "tests" / "c" / "abi_smoke.c"),
+           "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
