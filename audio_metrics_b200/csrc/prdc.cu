@@ -108,6 +108,16 @@ knn_refine_kernel(const T* __restrict__ X, long long ld, int d, long long n, lon
   const float band_f = filter_band(single_pass, nx_f, rho[i], max_norm);
   const float s_k = __shfl_sync(0xffffffffu, sel_key, k);      // +inf when fewer than k+1 candidates exist
   const float cut = s_k + 2.0f * band_f + 1e-6f * (fabsf(s_k) + nx_f);
+  // The other side: two candidates whose approximate keys differ by more than 2 band are in that order
+  // exactly.  With j0 the highest position <= k that follows such a gap, the j0 candidates in front of
+  // it are certainly the j0 nearest — their exact values are not needed, only that they rank first —
+  // and the (k+1)-th nearest is the (k+1-j0)-th among the rest.  With a band of 1e-3 of the typical
+  // spacing that leaves one or two rows to gather per row instead of k+1.
+  const float prev_key = __shfl_up_sync(0xffffffffu, sel_key, 1);
+  const bool gap = lane >= 1 && lane <= k &&
+                   (sel_key - prev_key) > 2.0f * band_f + 1e-6f * (fabsf(sel_key) + fabsf(prev_key) + nx_f);
+  const unsigned gaps = __ballot_sync(0xffffffffu, gap);
+  const int j0 = gaps ? 31 - __clz(gaps) : 0;
   double my_d2 = __longlong_as_double(0x7ff0000000000000ll);
   int n_sel = 0;
   for (int c = 0; c < Kt; ++c) {
@@ -115,6 +125,10 @@ knn_refine_kernel(const T* __restrict__ X, long long ld, int d, long long n, lon
     if (col < 0) break;
     const float key_c = __shfl_sync(0xffffffffu, sel_key, c);
     n_sel = c + 1;
+    if (c < j0) {                                               // certainly among the j0 nearest: ranks first
+      if (lane == c) my_d2 = -__longlong_as_double(0x7ff0000000000000ll);
+      continue;
+    }
     if (key_c > cut) continue;                                  // stays +inf: never among the k+1 smallest
     const double d2 = exact_sqdist_warp(xi, X + static_cast<long long>(col) * ld, d, lane);
     if (lane == c) my_d2 = d2;
