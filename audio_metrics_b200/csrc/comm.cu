@@ -96,7 +96,7 @@ extern "C" {
 int amb_comm_init(const int* devs, int n_dev, amb_comm_t** out) {
   if (!devs || n_dev < 1 || n_dev > 64 || !out) return set_error(AMB_ERR_ARG, "amb_comm_init: bad argument");
   const NcclApi* a = nccl_api();
-  if (!a) return set_error(AMB_ERR_CUDA, "amb_comm_init: libnccl.so.2 not found (%s)", dlerror() ? "dlopen failed" : "symbols missing");
+  if (!a) return set_error(AMB_ERR_CUDA, "amb_comm_init: NCCL is not available (dlopen of libnccl.so.2 / libnccl.so failed, or it lacks a symbol)");
   for (int i = 0; i < n_dev; ++i)
     for (int j = 0; j < i; ++j)
       if (devs[i] == devs[j]) return set_error(AMB_ERR_ARG, "amb_comm_init: device %d listed twice", devs[i]);
