@@ -255,12 +255,8 @@ struct TopkEpi {
       }
       if (__builtin_expect(!__any_sync(0xffffffffu, gm != 0), 1)) return;
     }
-    // Some row of the warp may take new candidates.  Per group that can hold one: each thread
-    // evaluates its 8 keys, builds the bit mask of those below its threshold, parks the keys in its
-    // private shared-memory slots, and the warp loops while any lane still has a bit to consume
-    // (usually one trip): a lane picks its lowest set column, reloads that key by dynamic index and
-    // inserts it; the list's last key tightens as it goes.
-    // Candidates are only PARKED here — (key, column) pairs in the thread's shared-memory slots — and
+    // Some row of the warp may take new candidates: per group that can hold one, each thread evaluates
+    // its 8 keys and the bit mask of those below its threshold.  Candidates are only PARKED here — (key, column) pairs in the thread's shared-memory slots — and
     // inserted by drain() once the engine has handed the accumulator back to the MMA warp
     // (tile_end).  Measured: the scan alone never delays the next tile, the inserts did — a warp
     // that met candidates in several chunks of one tile held the accumulator (and through the pair
